@@ -1,0 +1,169 @@
+"""Seeded synthetic svGPFA problem instances.
+
+One generator feeds the oracle, the golden-vector script, the parity tests and
+``bench.py`` so that every arm sees the same numbers.  A *case* is a plain dict
+of numpy arrays / python lists with the field names the reference's
+``initial_params`` dictionary uses (``/root/reference/src/svGPFA/utils/initUtils.py:468-481``):
+
+    kernel_types   list[K] of "expquad" | "periodic"
+    kernel_params  list[K] of float64 arrays, (1,) = [lengthscale] or (2,) = [lengthscale, period]
+    Z              list[K] of (R, M_k, 1)   inducing-point locations
+    m              list[K] of (R, M_k, 1)   variational means
+    chol_vecs      list[K] of (R, P_k, 1)   row-major lower-triangular entries of Ls
+    C (N, K), d (N, 1)                      linear embedding
+    leg_quad_points / leg_quad_weights      (R, Q, 1)
+    spike_times    (S,) float64 or float32, trial-major then neuron-major (the order
+                   ``PointProcessELL.__stackSpikeTimes`` produces,
+                   ``/root/reference/src/svGPFA/stats/expectedLogLikelihood.py:157-173``)
+    spike_counts   (R, N) int64             spikes of neuron n in trial r
+    reg            float                    prior-covariance regulariser
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# name -> (R, N, K, M, Q, mixed kernels, heavy ragged)   BASELINE.json "configs"
+CONFIGS = {
+    "tiny":    dict(R=4,     N=7,   K=3,  M=5,  Q=16,  mixed=True,  ragged=False),
+    "config2": dict(R=200,   N=100, K=3,  M=9,  Q=200, mixed=False, ragged=False),
+    "config3": dict(R=2000,  N=200, K=10, M=20, Q=200, mixed=True,  ragged=False),
+    "config4": dict(R=5000,  N=300, K=10, M=32, Q=200, mixed=False, ragged=True),
+    "config5": dict(R=20000, N=500, K=20, M=32, Q=200, mixed=False, ragged=False),
+}
+
+
+def leg_quad(Q: int, a: float, b: float):
+    """Gauss-Legendre nodes/weights on [a, b]; stands in for the un-vendored
+    ``gcnu_common.numerical_methods.utils.leggaussVarLimits`` called at
+    ``/root/reference/src/svGPFA/utils/miscUtils.py:234``."""
+    x, w = np.polynomial.legendre.leggauss(Q)
+    return 0.5 * (b - a) * x + 0.5 * (b + a), 0.5 * (b - a) * w
+
+
+def tril_size(M: int) -> int:
+    return M * (M + 1) // 2
+
+
+def make_params(R, N, K, M, Q, *, mixed=False, T=1.0, seed=0, reg=1e-3, M_list=None,
+                d_2d=True):
+    """Parameters only (no spikes).  ``M_list`` allows heterogeneous M_k."""
+    rng = np.random.default_rng(seed)
+    M_list = list(M_list) if M_list is not None else [M] * K
+    kernel_types, kernel_params, Z, m, chol_vecs = [], [], [], [], []
+    for k in range(K):
+        Mk = M_list[k]
+        if mixed and (k % 2 == 1):
+            kernel_types.append("periodic")
+            kernel_params.append(np.array([1.0 + 0.1 * k, 0.5 + 0.05 * k]))
+        else:
+            kernel_types.append("expquad")
+            kernel_params.append(np.array([0.1 + 0.05 * k]))
+        base = np.linspace(0.0, T, Mk)
+        Z.append((base[None, :] + rng.uniform(-0.1, 0.1, size=(R, Mk)) * T / Mk)[:, :, None])
+        m.append(rng.standard_normal((R, Mk, 1)))
+        Pk = tril_size(Mk)
+        rows, cols = np.tril_indices(Mk)
+        diag_mask = (rows == cols).astype(np.float64)
+        chol_vecs.append((0.1 * diag_mask[None, :] + 0.01 * rng.standard_normal((R, Pk)))[:, :, None])
+    rate = rng.uniform(5.0, 35.0, size=N)
+    C = 0.3 * rng.standard_normal((N, K))
+    d = np.log(rate) + 0.1 * rng.standard_normal(N)
+    d = d[:, None] if d_2d else d
+    x, w = leg_quad(Q, 0.0, T)
+    return dict(
+        kernel_types=kernel_types, kernel_params=kernel_params, Z=Z, m=m, chol_vecs=chol_vecs,
+        C=C, d=d,
+        leg_quad_points=np.repeat(x[None, :, None], R, axis=0),
+        leg_quad_weights=np.repeat(w[None, :, None], R, axis=0),
+        reg=float(reg), T=float(T), rate=rate,
+    )
+
+
+def make_spikes(R, N, *, T=1.0, seed=0, ragged=False, rate=None, dtype=np.float64):
+    """Poisson counts per (trial, neuron) and sorted-uniform spike times, flattened in
+    trial-major / neuron-major order."""
+    rng = np.random.default_rng(seed + 7919)
+    if ragged:
+        rate_n = np.exp(rng.uniform(np.log(1.0), np.log(200.0), size=N))
+        g_r = rng.lognormal(0.0, 0.5, size=R)
+    else:
+        rate_n = rate if rate is not None else rng.uniform(5.0, 35.0, size=N)
+        g_r = np.ones(R)
+    counts = rng.poisson(g_r[:, None] * rate_n[None, :] * T).astype(np.int64)
+    S = int(counts.sum())
+    times = rng.uniform(0.0, T, size=S)
+    # sort within each (trial, neuron) segment: add the segment id (times < T) and sort once
+    seg = np.repeat(np.arange(R * N, dtype=np.float64), counts.reshape(-1))
+    order = np.argsort(seg * (2.0 * T) + times, kind="stable")
+    times = times[order]
+    return times.astype(dtype), counts
+
+
+def make_case(name_or_cfg="tiny", *, seed=0, reg=1e-3, R=None, spike_dtype=np.float64,
+              M_list=None, d_2d=True):
+    cfg = dict(CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
+    if R is not None:
+        cfg["R"] = R
+    case = make_params(cfg["R"], cfg["N"], cfg["K"], cfg["M"], cfg["Q"], mixed=cfg["mixed"],
+                       seed=seed, reg=reg, M_list=M_list, d_2d=d_2d)
+    times, counts = make_spikes(cfg["R"], cfg["N"], T=case["T"], seed=seed, ragged=cfg["ragged"],
+                                rate=case["rate"], dtype=spike_dtype)
+    case["spike_times"] = times
+    case["spike_counts"] = counts
+    return case
+
+
+def nested_spikes(case):
+    """``measurements[r][n]`` as the reference's ``setMeasurements`` expects it
+    (``/root/reference/src/svGPFA/stats/svLowerBound.py:16-24``)."""
+    counts = case["spike_counts"]
+    R, N = counts.shape
+    pieces = np.split(case["spike_times"], np.cumsum(counts.reshape(-1))[:-1])
+    return [[pieces[r * N + n] for n in range(N)] for r in range(R)]
+
+
+def slice_trials(case, r0, r1):
+    """The sub-problem made of trials [r0, r1) (trial sharding)."""
+    counts = case["spike_counts"]
+    per_trial = counts.sum(axis=1)
+    off = np.concatenate([[0], np.cumsum(per_trial)])
+    out = dict(case)
+    for key in ("Z", "m", "chol_vecs"):
+        out[key] = [a[r0:r1] for a in case[key]]
+    for key in ("leg_quad_points", "leg_quad_weights"):
+        out[key] = case[key][r0:r1]
+    out["spike_counts"] = counts[r0:r1]
+    out["spike_times"] = case["spike_times"][off[r0]:off[r1]]
+    return out
+
+
+_LIST_KEYS = ("kernel_params", "Z", "m", "chol_vecs")
+
+
+def save_case(path, case, extra=None):
+    flat = {}
+    K = len(case["kernel_types"])
+    flat["kernel_types"] = np.array(case["kernel_types"])
+    for key in _LIST_KEYS:
+        for k in range(K):
+            flat[f"{key}_{k}"] = np.asarray(case[key][k])
+    for key in ("C", "d", "leg_quad_points", "leg_quad_weights", "spike_times", "spike_counts"):
+        flat[key] = np.asarray(case[key])
+    flat["reg"] = np.array(case["reg"])
+    for k, v in (extra or {}).items():
+        flat["out_" + k] = np.asarray(v)
+    np.savez_compressed(path, **flat)
+
+
+def load_case(path):
+    z = np.load(path, allow_pickle=False)
+    kt = [str(s) for s in z["kernel_types"]]
+    K = len(kt)
+    case = dict(kernel_types=kt)
+    for key in _LIST_KEYS:
+        case[key] = [z[f"{key}_{k}"] for k in range(K)]
+    for key in ("C", "d", "leg_quad_points", "leg_quad_weights", "spike_times", "spike_counts"):
+        case[key] = z[key]
+    case["reg"] = float(z["reg"])
+    extra = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    return case, extra

@@ -1,0 +1,80 @@
+"""The oracle (oracle/svgpfa_oracle.py) against fixtures produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only.
+
+Tolerances: the oracle repeats the reference's operations, so it must reproduce the
+reference's float64 outputs far inside the product tolerance of BASELINE.json
+(1e-10 ELBO, 1e-8 gradients): here 1e-13 / 1e-11.  The MATLAB pins use the tolerances of
+the reference's own unit tests.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names, rel_err
+from oracle import svgpfa_oracle as orc
+from svgpfa_b200 import synthetic
+
+GRAD_KEYS = ("grad_C", "grad_d")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference(name):
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, name + ".npz"))
+    with_stats = "quad_latent_mean" in ref
+    out = orc.elbo_and_grads(case, with_stats=with_stats)
+    assert abs(out["elbo"] - float(ref["elbo"])) <= 1e-13 * abs(float(ref["elbo"]))
+    assert abs(out["ell"] - float(ref["ell"])) <= 1e-13 * abs(float(ref["ell"]))
+    assert abs(out["kl"] - float(ref["kl"])) <= 1e-13 * abs(float(ref["kl"]))
+    K = len(case["kernel_types"])
+    keys = list(GRAD_KEYS)
+    for k in range(K):
+        keys += [f"grad_m_{k}", f"grad_chol_vecs_{k}", f"grad_kernel_params_{k}", f"grad_Z_{k}"]
+    for key in keys:
+        assert rel_err(out[key], ref[key]) <= 1e-11, key
+    if with_stats:
+        for key in ("quad_latent_mean", "quad_latent_var", "spike_latent_mean", "spike_latent_var",
+                    "quad_embedding_mean", "quad_embedding_var", "spike_embedding_mean"):
+            assert rel_err(out[key], ref[key]) <= 1e-12, key
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_spike_stacking_bit_exact(name):
+    """Indexing contract of PointProcessELL.__stackSpikeTimes (expectedLogLikelihood.py:157-173)."""
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, name + ".npz"))
+    times, idx = orc.stack_spike_times(synthetic.nested_spikes(case))
+    assert np.array_equal(np.concatenate([i.numpy() for i in idx]), ref["stacked_neuron_index"])
+    off = np.concatenate([[0], np.cumsum([len(t) for t in times])])
+    assert np.array_equal(off, ref["stacked_trial_offsets"])
+    t2, i2 = orc.case_spikes(case)
+    for a, b in zip(times, t2):
+        assert a.dtype == b.dtype and np.array_equal(a.numpy(), b.numpy())
+    for a, b in zip(idx, i2):
+        assert np.array_equal(a.numpy(), b.numpy())
+
+
+def test_matlab_known_answers():
+    """MATLAB values with the tolerances of the reference's own tests:
+    test_expectedLogLikelihood.py:16-104 (3e-4), test_klDivergence.py:13-62 (1e-5),
+    test_svLowerBound.py:18-106 (3e-4)."""
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "matlab_r5.npz"))
+    out = orc.elbo_and_grads(case)
+    assert abs(out["ell"] - float(ref["matlab_Elik"])) < 3e-4
+    assert abs(out["kl"] - float(ref["matlab_KLd"])) < 1e-5
+    assert abs(out["elbo"] + float(ref["matlab_obj"])) < 3e-4
+    # the reference's own float64 values recorded in SURVEY.md §8c
+    assert abs(out["ell"] - (-5499.8365087488119)) < 1e-9
+    assert abs(out["kl"] - 537.65708513673439) < 1e-9
+    assert abs(out["elbo"] - (-6037.493593885546)) < 1e-9
+
+
+def test_cached_stats_ell():
+    import torch
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed.npz"))
+    counts = case["spike_counts"].sum(axis=1)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    mu_s = [torch.from_numpy(ref["spike_latent_mean"][off[r]:off[r + 1]]) for r in range(len(counts))]
+    v = orc.ell_from_cached_stats(case, torch.from_numpy(ref["quad_latent_mean"]),
+                                  torch.from_numpy(ref["quad_latent_var"]), mu_s,
+                                  torch.from_numpy(case["C"]), torch.from_numpy(case["d"]))
+    assert abs(v.item() - float(ref["ell_cached"])) <= 1e-12 * abs(float(ref["ell_cached"]))
