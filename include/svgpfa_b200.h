@@ -1,0 +1,218 @@
+/*
+ * svgpfa_b200.h -- C ABI of the B200-native svGPFA lower-bound hot path.
+ *
+ * The reference (joacorapela/svGPFA) is pure Python/PyTorch and has NO FFI; its seam for this
+ * path is the duck-typed model protocol that SVEM_PyTorch drives.  This header
+ * is the boundary a maintainer would bind from Python (ctypes/cffi) underneath that protocol:
+ * plain pointers and sizes, no torch types.  Each entry point cites the reference code whose
+ * arithmetic it replaces (paths relative to /root/reference/src/svGPFA/).
+ *
+ * Conventions
+ *   - every pointer in svgpfa_buffers is a DEVICE pointer unless the field name ends in _host;
+ *   - the library never allocates, frees or keeps caller memory across calls; it is re-entrant
+ *     per stream; `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = launched OK, <0 = SVGPFA_E_* (bad argument / CUDA launch error).
+ *     Numerical failure (non-positive-definite Kzz, the reference's torch.linalg.LinAlgError at
+ *     utils/miscUtils.py:215) is reported asynchronously through buffers.info[0..3];
+ *   - all arithmetic is IEEE float64.
+ *
+ * Data layout (R trials of this shard, N neurons, K latents, Q quadrature points, M_k inducing
+ * points of latent k, P_k = M_k(M_k+1)/2):
+ *   parameters & their gradients, "K-major", exactly the memory of the reference's list-of-K
+ *   tensors laid end to end:   Z, m : [k][r][j]   offset R*moff[k] + r*M_k + j
+ *                              cholvec: [k][r][p] offset R*poff[k] + r*P_k + p  (row-major tril order,
+ *                                                 utils/miscUtils.py:135-139)
+ *                              theta  : [thoff[k] + i]    C: [n][k]    d: [n]
+ *   per-(trial, latent) workspace, "trial-major":
+ *                              vectors  [r][moff[k] + j]            (length R*KM)
+ *                              matrices [r][mmoff[k] + i*M_k + j]   (length R*MM)
+ *   quadrature statistics      [r][q][k]  (the reference's (R,Q,K) layout, svPosteriorOnLatents.py:190-193)
+ *   spikes                     spike_t[s] float64, trial-major then neuron-major -- the order of
+ *                              PointProcessELL.__stackSpikeTimes (expectedLogLikelihood.py:157-173);
+ *                              seg_off[r*N + n] .. seg_off[r*N + n + 1] = spikes of neuron n in trial r.
+ */
+#ifndef SVGPFA_B200_H
+#define SVGPFA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGPFA_ABI_VERSION 1
+#define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
+
+enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
+
+/* which gradient groups a call must produce (honour needs_input_grad) */
+enum {
+    SVGPFA_GRAD_POSTERIOR = 1,     /* m, cholvec           (E-step,            svEM.py:218-223) */
+    SVGPFA_GRAD_EMBEDDING = 2,     /* C, d                 (embedding M-step,  svEM.py:225-232) */
+    SVGPFA_GRAD_KERNEL    = 4,     /* theta                (kernels M-step,    svEM.py:234-254) */
+    SVGPFA_GRAD_INDLOCS   = 8,     /* Z                    (ind.-points M-step, svEM.py:256-264) */
+    SVGPFA_GRAD_ALL       = 15,
+    SVGPFA_REUSE_KZZ      = 16,    /* L, Li, logdet already valid for the current (Z, theta)   */
+    SVGPFA_REUSE_SPIKE    = 32     /* abar_spk already valid for the current (Z, theta, C)     */
+};
+
+enum {
+    SVGPFA_OK = 0, SVGPFA_E_ARG = -1, SVGPFA_E_CUDA = -2, SVGPFA_E_UNSUPPORTED = -3,
+    SVGPFA_INFO_NOT_PD = 1        /* value of info[0] when a Kzz was not positive definite */
+};
+
+/* One row per latent, int32[8], device and host copies (see svgpfa_dims.desc_host). */
+typedef struct svgpfa_latent_desc {
+    int32_t ktype;   /* SVGPFA_KERNEL_*            */
+    int32_t M;       /* inducing points            */
+    int32_t moff;    /* sum of M over previous k   */
+    int32_t mmoff;   /* sum of M*M over previous k */
+    int32_t poff;    /* sum of P over previous k   */
+    int32_t thoff;   /* sum of #params over previous k */
+    int32_t P;       /* M(M+1)/2                   */
+    int32_t nth;     /* 1 (expquad) or 2 (periodic)*/
+} svgpfa_latent_desc;
+
+typedef struct svgpfa_dims {
+    int32_t R, N, K, Q;
+    int32_t KM, MM, PP, TH;       /* sums over latents of M, M*M, P, #params */
+    int32_t Mmax, n_ntiles;       /* n_ntiles = ceil(N / SVGPFA_EMBED_TN): neuron tiles of quad_embed */
+    int64_t S;                    /* spikes in this shard */
+    double  reg;                  /* prior-covariance regulariser (kernelsMatricesStore.py:113-116) */
+    const svgpfa_latent_desc* desc_host;   /* HOST pointer, K rows */
+} svgpfa_dims;
+
+#define SVGPFA_EMBED_TN 128
+
+typedef struct svgpfa_buffers {
+    /* ---- inputs ------------------------------------------------------------------------- */
+    const svgpfa_latent_desc* desc;  /* K rows                                                  */
+    const double* kscale;        /* [K][4]: scale^2, 1/lengthscaleScale, 1/periodScale, 0 (kernels.py:29-31,37,75-76) */
+    const double* theta;         /* TH                                                          */
+    const double* Z;             /* R*KM   K-major                                              */
+    const double* m;             /* R*KM   K-major                                              */
+    const double* cholvec;       /* R*PP   K-major                                              */
+    const double* C;             /* N*K                                                         */
+    const double* d;             /* N                                                           */
+    const double* tq;            /* R*Q    quadrature nodes                                     */
+    const double* wq;            /* R*Q    quadrature weights                                   */
+    const double* spike_t;       /* S                                                           */
+    const int64_t* seg_off;      /* R*N+1                                                       */
+    const double* spike_cnt;     /* N      spikes of neuron n summed over the shard's trials    */
+    /* ---- per-(trial,latent) workspace --------------------------------------------------- */
+    double* L;                   /* R*MM  chol(Kzz)                                             */
+    double* Li;                  /* R*MM  L^-1 (lower)                                          */
+    double* X;                   /* R*MM  L^-1 Ls (lower)                                       */
+    double* c;                   /* R*KM  L^-1 m                                                */
+    double* alpha;               /* R*KM  Kzz^-1 m                                              */
+    double* logdetL;             /* R*K   sum_i log L_ii                                        */
+    double* kl_rk;               /* R*K                                                         */
+    double* A_q;                 /* R*MM  sum_q varbar_q v_q v_q^T (lower incl. diag)           */
+    double* abar_q;              /* R*KM  sum_q mubar_q k_q                                     */
+    double* abar_spk;            /* R*KM  sum_s C[n_s,k] kappa(t_s, z_j)                        */
+    double* dz_acc;              /* R*KM  dELBO/dZ contributions of the quadrature and spike terms */
+    double* dth_part;            /* R*TH  per-trial dELBO/dtheta partials                       */
+    /* ---- quadrature statistics ---------------------------------------------------------- */
+    double* mu_q;                /* R*Q*K */
+    double* var_q;               /* R*Q*K */
+    double* mubar_part;          /* n_ntiles*R*Q*K  per-neuron-tile partials of dELBO/dmu_q     */
+    double* varbar_part;         /* n_ntiles*R*Q*K                                              */
+    double* term1_part;          /* SVGPFA_TERM1_SLOTS partial sums of the intensity integral  */
+    /* ---- cached-statistics path (embedding M-step) -------------------------------------- */
+    double* mu_s;                /* S*K   latent means at spike times, [s][k]                   */
+    /* ---- outputs ------------------------------------------------------------------------ */
+    double* shared;              /* SVGPFA_SHARED_HDR + N*K + N + TH: [elbo, ell, kl, term1, term2, 0,0,0 | dC | dd | dtheta]
+                                    -- the buffer a multi-GPU caller all-reduces */
+    double* gZ;                  /* R*KM  K-major */
+    double* gm;                  /* R*KM  K-major */
+    double* gcholvec;            /* R*PP  K-major */
+    int32_t* info;               /* 4: [status, r, k, 0] */
+} svgpfa_buffers;
+
+#define SVGPFA_SHARED_HDR 8
+#define SVGPFA_TERM1_SLOTS 4096
+
+int svgpfa_abi_version(void);
+const char* svgpfa_last_error(void);
+
+/* (i)+(ii)  Kzz = kappa(Z,Z) + reg I, L = chol(Kzz), Li = L^-1, logdetL.
+ * Replaces IndPointsLocsKMS.buildKernelsMatrices + IndPointsLocsKMS_Chol._invertKzz3D
+ * (stats/kernelsMatricesStore.py:107-128) and miscUtils.chol3D (utils/miscUtils.py:209-216). */
+int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+
+/* (ii)+(v)  Ls = unpack(cholvec), X = Li Ls, c = Li m, alpha = Li^T c, KL_rk.
+ * Replaces SVPosteriorOnIndPointsChol.buildCov (stats/svPosteriorOnIndPoints.py:47-49,
+ * utils/miscUtils.py:135-155), IndPointsLocsKMS_Chol.solveForLatent (kernelsMatricesStore.py:132-138)
+ * and KLDivergence._evalSumAcrossTrials (stats/klDivergence.py:31-44). */
+int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+
+/* (i)+(iii) latent posterior mean/variance at the Legendre quadrature points.
+ * Replaces IndPointsLocsAndAllTimesKMS.buildKernelsMatrices (kernelsMatricesStore.py:186-195) and
+ * SVPosteriorOnLatentsAllTimes.__computeMeansAndVarsGivenKernelMatrices (svPosteriorOnLatents.py:185-216);
+ * Ktz (R,Q,M) is never materialised. */
+int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+
+/* (iii) embedding + exp-link intensity integral + its adjoints (dC, dd into `shared`, mubar/varbar partials).
+ * Replaces LinearSVEmbeddingAllTimes._computeMeansAndVarsGivenSVPosteriorOnLatentsStats (svEmbedding.py:80-84),
+ * PointProcessELLExpLink._getELinkValues (expectedLogLikelihood.py:205-208) and the weighted sum at
+ * expectedLogLikelihood.py:122-131; eLinkValues (R,Q,N) is never materialised. */
+int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* (iii) adjoint of svgpfa_quad_latent_fwd: A_q, abar_q and (if KERNEL|INDLOCS) dz_acc, dth_part.
+ * The reference obtains these from torch.autograd (svEM.py:281). */
+int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* (i)+(iv) spike-time log-intensity term, value and every adjoint in one pass over the ragged CSR
+ * spikes: abar_spk, dC (into `shared`), dz_acc, dth_part.
+ * Replaces IndPointsLocsAndAssocTimesKMS.buildKernelsMatrices (kernelsMatricesStore.py:208-221),
+ * SVPosteriorOnLatentsAssocTimes.__compute... (svPosteriorOnLatents.py:265-300; the unused variance
+ * is not computed), LinearSVEmbeddingAssocTimes._compute... (svEmbedding.py:137-144) and
+ * PointProcessELLExpLink._getELogLinkValues (expectedLogLikelihood.py:210-213). */
+int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* (ii)+(v) adjoints through alpha, c, X, the KL term and the Cholesky factorisation: gm, gcholvec,
+ * gZ, dth_part.  The reference obtains these from torch.autograd. */
+int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* reductions into `shared`: elbo = -term1 + term2 - KL, dtheta = sum_r dth_part, dd += spike counts.
+ * Replaces SVLowerBound.eval (svLowerBound.py:47-54) and the sums at expectedLogLikelihood.py:132-134,
+ * klDivergence.py:18-29. */
+int svgpfa_finalize(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* The whole path: the eight calls above in order (zeroing accumulators first). One unit of work of
+ * the benchmark = this call with flags = SVGPFA_GRAD_ALL. */
+int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* (iv) cached-statistics path of the embedding M-step (svEM.py:225-232):
+ *   svgpfa_spike_latent_means   : mu_s[s][k] = kappa_k(t_s, Z_kr) . alpha_kr
+ *                                 (SVPosteriorOnLatentsAssocTimes.computeMeansAndVars, mean part)
+ *   svgpfa_cached_ell_fwd_bwd   : ELL(C, d | mu_q, var_q, mu_s) and dC, dd into `shared`
+ *                                 (PointProcessELL.evalSumAcrossTrialsAndNeurons with
+ *                                  svPosteriorOnLatentsStats, expectedLogLikelihood.py:107-135);
+ *                                 the spike part is the HBM-bound ragged gather over mu_s. */
+int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+
+/* Host helper: (r,n) segment offsets from per-segment spike counts, and the per-spike neuron index the
+ * reference builds (expectedLogLikelihood.py:168-172), for the bit-exact indexing check.
+ * counts_host[R*N] -> seg_off_host[R*N+1]; neuron_index_host may be NULL, else S entries (int64). */
+int svgpfa_build_segments_host(int32_t R, int32_t N, const int64_t* counts_host,
+                               int64_t* seg_off_host, int64_t* neuron_index_host);
+
+/* End-to-end entry with HOST buffers (pinned or pageable): copies parameters and spikes to the
+ * device, runs svgpfa_elbo_grad and copies `shared`, gZ, gm, gcholvec, info back.  `dev` supplies the
+ * device-side buffers (same struct, device pointers); every *_host array mirrors the device one. */
+typedef struct svgpfa_host_io {
+    const double* theta_host; const double* Z_host; const double* m_host; const double* cholvec_host;
+    const double* C_host; const double* d_host; const double* tq_host; const double* wq_host;
+    const double* spike_t_host; const int64_t* seg_off_host; const double* spike_cnt_host;
+    double* shared_host; double* gZ_host; double* gm_host; double* gcholvec_host; int32_t* info_host;
+    int32_t copy_static;      /* 1: also copy tq, wq, spikes, segments (first call); 0: parameters only */
+} svgpfa_host_io;
+int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
+                          uint32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGPFA_B200_H */

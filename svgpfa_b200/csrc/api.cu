@@ -1,0 +1,206 @@
+// C-ABI glue: error reporting, the final reductions, the whole-path orchestrators (device and host
+// buffers) and the host-side segment builder.  See include/svgpfa_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t stream);
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+// ------------------------------------------------------------------------------------------
+// reductions into `shared`
+//   shared[2] = KL, shared[3] = term1, shared[4] += alpha . abar_spk + cnt . d, dtheta = sum_r dth_part,
+//   dd += spike counts
+// ------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+
+__global__ void __launch_bounds__(FIN_THREADS) finalize_reduce_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
+                                                                      int use_abar) {
+    __shared__ double red[32];
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gstr = (size_t)gridDim.x * blockDim.x;
+    double kl = 0.0, t1 = 0.0, t2 = 0.0;
+    for (size_t i = gtid; i < (size_t)dm.R * dm.K; i += gstr) kl += bf.kl_rk[i];
+    for (size_t i = gtid; i < SVGPFA_TERM1_SLOTS; i += gstr) t1 += bf.term1_part[i];
+    if (use_abar)
+        for (size_t i = gtid; i < (size_t)dm.R * dm.KM; i += gstr) t2 = fma(bf.alpha[i], bf.abar_spk[i], t2);
+    double* gd = bf.shared + SVGPFA_SHARED_HDR + (size_t)dm.N * dm.K;
+    for (size_t n = gtid; n < (size_t)dm.N; n += gstr) {
+        t2 = fma(bf.spike_cnt[n], bf.d[n], t2);
+        if (flags & SVGPFA_GRAD_EMBEDDING) gd[n] += bf.spike_cnt[n];
+    }
+    const double skl = block_sum(kl, red);
+    const double st1 = block_sum(t1, red);
+    const double st2 = block_sum(t2, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(bf.shared + 2, skl);
+        atomicAdd(bf.shared + 3, st1);
+        atomicAdd(bf.shared + 4, st2);
+    }
+    if (flags & SVGPFA_GRAD_KERNEL) {
+        // dtheta[i] = sum_r dth_part[r][i]: one warp per parameter, lanes stride over trials
+        double* gth = gd + dm.N;
+        const int wid = (int)(gtid >> 5), lane = threadIdx.x & 31, nw = (int)(gstr >> 5);
+        for (int i = wid; i < dm.TH; i += nw) {
+            double s = 0.0;
+            for (int r = lane; r < dm.R; r += 32) s += bf.dth_part[(size_t)r * dm.TH + i];
+            s = warp_sum(s);
+            if (lane == 0) gth[i] = s;
+        }
+    }
+}
+
+__global__ void finalize_combine_kernel(svgpfa_buffers bf, int with_kl) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double* s = bf.shared;
+        const double ell = -s[3] + s[4];
+        s[1] = ell;
+        s[0] = with_kl ? ell - s[2] : ell;
+    }
+}
+
+int check_dims(const svgpfa_dims* d, const svgpfa_buffers* b, const char* where) {
+    if (!d || !b) return svgpfa_set_error(SVGPFA_E_ARG, where, cudaSuccess);
+    if (d->R < 0 || d->N < 0 || d->K < 1 || d->Q < 0 || d->Mmax < 1 || d->Mmax > SVGPFA_MAX_M)
+        return svgpfa_set_error(SVGPFA_E_ARG, where, cudaSuccess);
+    return SVGPFA_OK;
+}
+
+size_t shared_len(const svgpfa_dims* d) { return SVGPFA_SHARED_HDR + (size_t)d->N * d->K + d->N + d->TH; }
+
+}  // namespace
+
+int svgpfa_set_error(int code, const char* where, cudaError_t ce) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, ce == cudaSuccess ? (code == SVGPFA_E_ARG ? "bad argument" : "unsupported") : cudaGetErrorString(ce));
+    return code;
+}
+
+extern "C" int svgpfa_abi_version(void) { return SVGPFA_ABI_VERSION; }
+extern "C" const char* svgpfa_last_error(void) { return g_err; }
+
+extern "C" int svgpfa_finalize(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
+    int rc = check_dims(dims, buf, "finalize");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t work = (size_t)dims->R * dims->KM;
+    int blocks = (int)((work + FIN_THREADS * 8 - 1) / (FIN_THREADS * 8));
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;
+    finalize_reduce_kernel<<<blocks, FIN_THREADS, 0, st>>>(*dims, *buf, flags, 1);
+    SVGPFA_CHECK_LAUNCH("finalize_reduce");
+    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, 1);
+    SVGPFA_CHECK_LAUNCH("finalize_combine");
+    return SVGPFA_OK;
+}
+
+extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
+    int rc = check_dims(dims, buf, "elbo_grad");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t lat = SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
+    const uint32_t kz = SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
+    const bool reuse_spike = (flags & SVGPFA_REUSE_SPIKE) && !(flags & (kz | SVGPFA_GRAD_EMBEDDING));
+    cudaMemsetAsync(buf->shared, 0, sizeof(double) * shared_len(dims), st);
+    cudaMemsetAsync(buf->term1_part, 0, sizeof(double) * SVGPFA_TERM1_SLOTS, st);
+    cudaMemsetAsync(buf->info, 0, sizeof(int32_t) * 4, st);
+    if (!reuse_spike) cudaMemsetAsync(buf->abar_spk, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
+    if (flags & kz) {
+        cudaMemsetAsync(buf->dz_acc, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
+        cudaMemsetAsync(buf->dth_part, 0, sizeof(double) * (size_t)dims->R * dims->TH, st);
+    }
+    if (!(flags & SVGPFA_REUSE_KZZ)) { rc = svgpfa_kzz_chol_fwd(dims, buf, stream); if (rc) return rc; }
+    rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc;
+    rc = svgpfa_quad_latent_fwd(dims, buf, stream); if (rc) return rc;
+    rc = svgpfa_quad_embed_fwd_bwd(dims, buf, flags, stream); if (rc) return rc;
+    if (flags & lat) { rc = svgpfa_quad_latent_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    if (!reuse_spike) { rc = svgpfa_spike_fwd_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    if (flags & lat) { rc = svgpfa_indpoints_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    return svgpfa_finalize(dims, buf, flags, stream);
+}
+
+extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
+    int rc = check_dims(dims, buf, "cached_ell_fwd_bwd");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(buf->shared, 0, sizeof(double) * shared_len(dims), st);
+    cudaMemsetAsync(buf->term1_part, 0, sizeof(double) * SVGPFA_TERM1_SLOTS, st);
+    rc = svgpfa_quad_embed_fwd_bwd(dims, buf, SVGPFA_GRAD_EMBEDDING, stream); if (rc) return rc;
+    rc = svgpfa_launch_spike_gather(dims, buf, st); if (rc) return rc;
+    // term1 and the d part of term2; no KL, no alpha.abar (the gather produced the C part)
+    svgpfa_dims d0 = *dims;
+    d0.R = 0;                                   // empties the kl_rk loop; the alpha.abar loop is off (use_abar = 0)
+    finalize_reduce_kernel<<<8, FIN_THREADS, 0, st>>>(d0, *buf, SVGPFA_GRAD_EMBEDDING, 0);
+    SVGPFA_CHECK_LAUNCH("cached finalize_reduce");
+    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, 0);
+    SVGPFA_CHECK_LAUNCH("cached finalize_combine");
+    return SVGPFA_OK;
+}
+
+extern "C" int svgpfa_build_segments_host(int32_t R, int32_t N, const int64_t* counts_host, int64_t* seg_off_host,
+                                          int64_t* neuron_index_host) {
+    if (R < 0 || N < 0 || !counts_host || !seg_off_host) return svgpfa_set_error(SVGPFA_E_ARG, "build_segments_host", cudaSuccess);
+    int64_t acc = 0;
+    seg_off_host[0] = 0;
+    for (int64_t i = 0; i < (int64_t)R * N; ++i) {
+        const int64_t c = counts_host[i];
+        if (c < 0) return svgpfa_set_error(SVGPFA_E_ARG, "build_segments_host: negative count", cudaSuccess);
+        if (neuron_index_host) {
+            const int64_t n = i % N;
+            for (int64_t s = 0; s < c; ++s) neuron_index_host[acc + s] = n;
+        }
+        acc += c;
+        seg_off_host[i + 1] = acc;
+    }
+    return SVGPFA_OK;
+}
+
+extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
+                                     uint32_t flags, void* stream) {
+    int rc = check_dims(dims, dev, "elbo_grad_host");
+    if (rc) return rc;
+    if (!io) return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t R = dims->R, D = sizeof(double);
+#define H2D(dst, src, bytes)                                                                          \
+    do {                                                                                              \
+        if ((bytes) > 0) {                                                                            \
+            cudaError_t e = cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st); \
+            if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host H2D", e);     \
+        }                                                                                             \
+    } while (0)
+#define D2H(dst, src, bytes)                                                                          \
+    do {                                                                                              \
+        if ((bytes) > 0 && (dst)) {                                                                   \
+            cudaError_t e = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st);        \
+            if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host D2H", e);     \
+        }                                                                                             \
+    } while (0)
+    if (io->copy_static) {
+        H2D(dev->tq, io->tq_host, R * dims->Q * D);
+        H2D(dev->wq, io->wq_host, R * dims->Q * D);
+        H2D(dev->spike_t, io->spike_t_host, (size_t)dims->S * D);
+        H2D(dev->seg_off, io->seg_off_host, (R * dims->N + 1) * sizeof(int64_t));
+        H2D(dev->spike_cnt, io->spike_cnt_host, (size_t)dims->N * D);
+    }
+    H2D(dev->theta, io->theta_host, (size_t)dims->TH * D);
+    H2D(dev->Z, io->Z_host, R * dims->KM * D);
+    H2D(dev->m, io->m_host, R * dims->KM * D);
+    H2D(dev->cholvec, io->cholvec_host, R * dims->PP * D);
+    H2D(dev->C, io->C_host, (size_t)dims->N * dims->K * D);
+    H2D(dev->d, io->d_host, (size_t)dims->N * D);
+    rc = svgpfa_elbo_grad(dims, dev, flags, stream);
+    if (rc) return rc;
+    D2H(io->shared_host, dev->shared, shared_len(dims) * D);
+    if (flags & SVGPFA_GRAD_INDLOCS) D2H(io->gZ_host, dev->gZ, R * dims->KM * D);
+    if (flags & SVGPFA_GRAD_POSTERIOR) {
+        D2H(io->gm_host, dev->gm, R * dims->KM * D);
+        D2H(io->gcholvec_host, dev->gcholvec, R * dims->PP * D);
+    }
+    D2H(io->info_host, dev->info, 4 * sizeof(int32_t));
+#undef H2D
+#undef D2H
+    return SVGPFA_OK;
+}

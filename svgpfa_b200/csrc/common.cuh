@@ -1,0 +1,112 @@
+// Shared device helpers for the svGPFA lower-bound kernels (sm_100a, float64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "svgpfa_b200.h"
+
+#define SVGPFA_PI 3.14159265358979323846
+
+// Per-latent kernel constants derived from theta (kernels.py:33-46, 73-85).
+//   expquad : kappa = s2 exp(nh d^2),            nh = -0.5 / l^2
+//   periodic: kappa = s2 exp(nh sin^2(pi d/p)),  nh = -2 / l^2
+// l = theta[0] / lengthscaleScale, p = theta[1] / periodScale.
+struct KConst {
+    int type;
+    double s2;      // scale^2
+    double nh;      // see above
+    double invp;    // periodic: 1/p
+    double dl;      // d kappa / d theta0 = kappa * q * dl,  q = d^2 (expquad) or sin^2 (periodic)
+    double dp;      // periodic: d kappa / d theta1 = kappa * sin(2 pi d/p) * d * dp
+    double dd;      // d kappa / d delta = kappa * (d or sin(2 pi d/p)) * dd
+};
+
+__device__ __forceinline__ KConst make_kconst(const svgpfa_latent_desc& ds, const double* __restrict__ theta,
+                                              const double* __restrict__ kscale, int k) {
+    KConst kc;
+    kc.type = ds.ktype;
+    kc.s2 = kscale[4 * k + 0];
+    const double ils = kscale[4 * k + 1];
+    const double l = theta[ds.thoff] * ils;
+    if (ds.ktype == SVGPFA_KERNEL_EXPQUAD) {
+        kc.nh = -0.5 / (l * l);
+        kc.invp = 0.0;
+        kc.dl = ils / (l * l * l);
+        kc.dp = 0.0;
+        kc.dd = -1.0 / (l * l);
+    } else {
+        const double ips = kscale[4 * k + 2];
+        const double p = theta[ds.thoff + 1] * ips;
+        kc.nh = -2.0 / (l * l);
+        kc.invp = 1.0 / p;
+        kc.dl = 4.0 * ils / (l * l * l);
+        kc.dp = ips * 2.0 * SVGPFA_PI / (l * l * p * p);
+        kc.dd = -2.0 * SVGPFA_PI / (p * l * l);
+    }
+    return kc;
+}
+
+// kappa(delta) only.
+__device__ __forceinline__ double kappa_val(const KConst& kc, double delta) {
+    double q;
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+        q = delta * delta;
+    } else {
+        const double s = sinpi(delta * kc.invp);
+        q = s * s;
+    }
+    return kc.s2 * exp(kc.nh * q);
+}
+
+// kappa and its partial derivatives w.r.t. delta (= x - z), theta0 and theta1.
+__device__ __forceinline__ void kappa_grad(const KConst& kc, double delta, double& kv, double& dk_dd,
+                                           double& dk_dt0, double& dk_dt1) {
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+        const double q = delta * delta;
+        kv = kc.s2 * exp(kc.nh * q);
+        dk_dd = kv * delta * kc.dd;
+        dk_dt0 = kv * q * kc.dl;
+        dk_dt1 = 0.0;
+    } else {
+        double s, c;
+        sincospi(delta * kc.invp, &s, &c);
+        const double q = s * s;
+        const double s2x = 2.0 * s * c;
+        kv = kc.s2 * exp(kc.nh * q);
+        dk_dd = kv * s2x * kc.dd;
+        dk_dt0 = kv * q * kc.dl;
+        dk_dt1 = kv * s2x * delta * kc.dp;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` = shared scratch of >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int i = 0; i < nw; ++i) t += red[i];
+    }
+    return t;
+}
+
+__host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// host-side error plumbing (api.cu)
+int svgpfa_set_error(int code, const char* where, cudaError_t ce);
+#define SVGPFA_CHECK_LAUNCH(where)                                          \
+    do {                                                                    \
+        cudaError_t _e = cudaGetLastError();                                \
+        if (_e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, where, _e); \
+    } while (0)

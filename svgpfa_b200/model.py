@@ -1,0 +1,514 @@
+"""``B200SVLowerBound``: the model object ``SVEM_PyTorch.maximize`` drives, with the method
+names, argument meaning and error behaviour of the reference's ``SVLowerBound``
+(``/root/reference/src/svGPFA/stats/svLowerBound.py:6-120``; protocol table in SURVEY.md §8b),
+whose arithmetic runs in the hand-written CUDA library behind ``include/svgpfa_b200.h``.
+
+Differences a user can observe, all deliberate:
+  * parameters live on the GPU; the getters return the leaf tensors the optimiser mutates in
+    place (views into one packed buffer per parameter group, so no gather/scatter per step);
+  * ``buildKernelsMatrices()`` only invalidates caches; matrices are rebuilt lazily inside
+    ``eval()`` when (Z, theta) actually changed (tensor version counters);
+  * value and gradients are produced by ONE fused forward+backward pass (the bound is a sum,
+    its upstream gradient is a scalar applied in ``backward``);
+  * a non-positive-definite Kzz raises ``torch.linalg.LinAlgError`` from ``eval()``
+    (the reference raises it from ``buildKernelsMatrices``, utils/miscUtils.py:215).
+There is no CPU path: without a CUDA device or without the built library every entry raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import warnings
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .kernels import kernel_spec
+
+_F64 = torch.float64
+
+
+def _tril_size(M):
+    return M * (M + 1) // 2
+
+
+class _LowerBoundFn(torch.autograd.Function):
+    """ELBO (or ELL from cached statistics) as one differentiable node over every leaf."""
+
+    @staticmethod
+    def forward(ctx, model, cached_stats, *leaves):
+        K = model._K
+        need = ctx.needs_input_grad[2:]
+        flags = 0
+        if any(need[0:2 * K]):
+            flags |= _cabi.GRAD_POSTERIOR
+        if any(need[2 * K:2 * K + 2]):
+            flags |= _cabi.GRAD_EMBEDDING
+        if any(need[2 * K + 2:3 * K + 2]):
+            flags |= _cabi.GRAD_KERNEL
+        if any(need[3 * K + 2:4 * K + 2]):
+            flags |= _cabi.GRAD_INDLOCS
+        if cached_stats is not None:
+            flags &= _cabi.GRAD_EMBEDDING
+            shared = model._run_cached(cached_stats)
+            gZ = gm = gcv = None
+        else:
+            shared, gZ, gm, gcv = model._run(flags)
+        ctx.model = model
+        ctx.flags = flags
+        ctx.bufs = (shared, gZ, gm, gcv)
+        ctx.d_shape = leaves[2 * K + 1].shape
+        return shared[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, flags = ctx.model, ctx.flags
+        shared, gZ, gm, gcv = ctx.bufs
+        K, R, N = model._K, model._R, model._N
+        need = ctx.needs_input_grad[2:]
+        grads = [None] * (4 * K + 2)
+        if flags & _cabi.GRAD_POSTERIOR:
+            sm, sc = gm * grad_out, gcv * grad_out
+            for k in range(K):
+                M, P = model._M[k], model._P[k]
+                if need[k]:
+                    grads[k] = sm[R * model._moff[k]:R * (model._moff[k] + M)].view(R, M, 1)
+                if need[K + k]:
+                    grads[K + k] = sc[R * model._poff[k]:R * (model._poff[k] + P)].view(R, P, 1)
+        if flags & (_cabi.GRAD_EMBEDDING | _cabi.GRAD_KERNEL):
+            ss = shared * grad_out
+            h = _cabi.SHARED_HDR
+            if need[2 * K]:
+                grads[2 * K] = ss[h:h + N * K].view(N, K)
+            if need[2 * K + 1]:
+                grads[2 * K + 1] = ss[h + N * K:h + N * K + N].view(ctx.d_shape)
+            if flags & _cabi.GRAD_KERNEL:
+                th = ss[h + N * K + N:]
+                for k in range(K):
+                    if need[2 * K + 2 + k]:
+                        grads[2 * K + 2 + k] = th[model._thoff[k]:model._thoff[k] + model._nth[k]]
+        if flags & _cabi.GRAD_INDLOCS:
+            sz = gZ * grad_out
+            for k in range(K):
+                if need[3 * K + 2 + k]:
+                    M = model._M[k]
+                    grads[3 * K + 2 + k] = sz[R * model._moff[k]:R * (model._moff[k] + M)].view(R, M, 1)
+        return (None, None, *grads)
+
+
+class B200SVLowerBound:
+    def __init__(self, kernels=None, device=None, process_group=None, check_errors=True):
+        self._device = torch.device(device) if device is not None else None
+        self._pg = process_group
+        self._check_errors = check_errors
+        self._kernels = None
+        self._reg = None
+        self._params_set = False
+        self._spikes_set = False
+        self._quad_set = False
+        self._ready = False
+        self._kzz_key = None
+        self._spike_key = None
+        self._bufs = None
+        if kernels is not None:
+            self.setKernels(kernels)
+
+    # ------------------------------------------------------------------ device / library
+    def _dev(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("svgpfa_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        if self._device.type != "cuda":
+            raise RuntimeError("svgpfa_b200 only runs on CUDA devices; there is no CPU fallback")
+        return self._device
+
+    def _to_dev(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().to(device=self._dev(), dtype=_F64)
+        return torch.as_tensor(np.asarray(x), dtype=_F64).to(self._dev())
+
+    # ------------------------------------------------------------------ setters (svLowerBound.py:13-45,83-99)
+    def setKernels(self, kernels):
+        self._kernels = list(kernels)
+        self._ready = False
+
+    def setInitialParams(self, initial_params):
+        """``initial_params`` as produced by ``svGPFA.utils.initUtils.getParamsAndKernelsTypes``
+        (utils/initUtils.py:468-481).  The tensors are copied into packed device buffers; the
+        getters return leaf views of those buffers."""
+        if self._kernels is None:
+            raise RuntimeError("setKernels must be called before setInitialParams")
+        pol = initial_params["posterior_on_latents"]
+        mean = pol["posterior_on_ind_points"]["mean"]
+        chol = pol["posterior_on_ind_points"]["cholVecs"]
+        kms = pol["kernels_matrices_store"]
+        theta0, Z0 = kms["kernels_params0"], kms["inducing_points_locs0"]
+        C0, d0 = initial_params["embedding"]["C0"], initial_params["embedding"]["d0"]
+        K = len(mean)
+        if not (len(chol) == K and len(theta0) == K and len(Z0) == K and len(self._kernels) == K):
+            raise ValueError("inconsistent number of latents in initial_params / kernels")
+        R = int(Z0[0].shape[0])
+        self._K, self._R = K, R
+        self._M = [int(Z0[k].shape[1]) for k in range(K)]
+        if max(self._M) > _cabi.MAX_M:
+            raise ValueError(f"at most {_cabi.MAX_M} inducing points per latent are supported")
+        self._P = [_tril_size(M) for M in self._M]
+        for k in range(K):
+            if tuple(mean[k].shape) != (R, self._M[k], 1) or tuple(chol[k].shape) != (R, self._P[k], 1) \
+                    or tuple(Z0[k].shape) != (R, self._M[k], 1):
+                raise ValueError(f"latent {k}: expected mean (R,M,1), cholVecs (R,P,1), locs (R,M,1)")
+        specs = [kernel_spec(kern) for kern in self._kernels]
+        self._nth = [2 if s[0] == _cabi.KERNEL_PERIODIC else 1 for s in specs]
+        for k in range(K):
+            if int(theta0[k].numel()) != self._nth[k]:
+                raise ValueError(f"latent {k}: kernel expects {self._nth[k]} parameters")
+        cum = lambda xs: [int(v) for v in np.concatenate([[0], np.cumsum(xs)])]
+        self._moff, self._poff, self._thoff = cum(self._M), cum(self._P), cum(self._nth)
+        self._mmoff = cum([M * M for M in self._M])
+        self._KM, self._PP, self._TH, self._MM = self._moff[-1], self._poff[-1], self._thoff[-1], self._mmoff[-1]
+        dev = self._dev()
+        pack = lambda xs: torch.cat([self._to_dev(x).reshape(-1) for x in xs]).contiguous()
+        self._Zbuf, self._mbuf, self._cvbuf, self._thbuf = pack(Z0), pack(mean), pack(chol), pack(theta0)
+        self._Z = [self._Zbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
+        self._m = [self._mbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
+        self._cv = [self._cvbuf[R * self._poff[k]:R * self._poff[k + 1]].view(R, self._P[k], 1) for k in range(K)]
+        self._theta = [self._thbuf[self._thoff[k]:self._thoff[k + 1]] for k in range(K)]
+        for k, kern in enumerate(self._kernels):
+            if hasattr(kern, "setParams"):
+                kern.setParams(self._theta[k])
+        self._C = self._to_dev(C0).contiguous().clone()
+        self._d = self._to_dev(d0).contiguous().clone()
+        self._N = int(self._C.shape[0])
+        if self._C.shape[1] != K or self._d.numel() != self._N:
+            raise ValueError("C must be (N,K) and d must have N entries")
+        desc = (_cabi.LatentDesc * K)()
+        for k in range(K):
+            desc[k] = _cabi.LatentDesc(specs[k][0], self._M[k], self._moff[k], self._mmoff[k], self._poff[k],
+                                       self._thoff[k], self._P[k], self._nth[k])
+        self._desc_host = desc
+        self._desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.int32).to(dev)
+        self._kscale = torch.tensor([[s[1], s[2], s[3], 0.0] for s in specs], dtype=_F64).to(dev).contiguous()
+        self._params_set = True
+        self._ready = False
+        self._kzz_key = self._spike_key = None
+
+    def setMeasurements(self, measurements):
+        """``measurements[r][n]`` = spike times of neuron n in trial r (list / array / tensor, float32
+        or float64).  Stacked trial-major, neuron-major, within-neuron order kept -- the order of
+        ``PointProcessELL.__stackSpikeTimes`` (stats/expectedLogLikelihood.py:157-173)."""
+        R = len(measurements)
+        N = len(measurements[0]) if R else 0
+        counts = np.zeros((R, N), dtype=np.int64)
+        pieces = []
+        for r in range(R):
+            if len(measurements[r]) != N:
+                raise ValueError("every trial must list the same number of neurons")
+            for n in range(N):
+                s = measurements[r][n]
+                s = s.detach().cpu().numpy() if isinstance(s, torch.Tensor) else np.asarray(s)
+                s = s.reshape(-1)
+                counts[r, n] = s.size
+                if s.size:
+                    pieces.append(s.astype(np.float64))      # float32 -> float64 is exact
+        times = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.float64)
+        self.setMeasurementsFlat(times, counts)
+
+    def setMeasurementsFlat(self, spike_times, spike_counts):
+        """Same data already stacked: ``spike_times`` (S,) in the order described above and
+        ``spike_counts`` (R, N).  Accepts host or device arrays."""
+        dev = self._dev()
+        if isinstance(spike_counts, torch.Tensor):
+            counts_dev = spike_counts.to(device=dev, dtype=torch.int64).contiguous()
+            R, N = counts_dev.shape
+            seg = torch.zeros(R * N + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(counts_dev.reshape(-1), 0, out=seg[1:])
+            cnt = counts_dev.sum(0).to(_F64)
+        else:
+            counts = np.ascontiguousarray(np.asarray(spike_counts, dtype=np.int64))
+            R, N = counts.shape
+            seg_host = np.empty(R * N + 1, dtype=np.int64)
+            _cabi.check(_cabi.lib().svgpfa_build_segments_host(
+                R, N, counts.ctypes.data, seg_host.ctypes.data, None), "build_segments_host")
+            seg = torch.from_numpy(seg_host).to(dev)
+            cnt = torch.from_numpy(counts.sum(0).astype(np.float64)).to(dev)
+        if isinstance(spike_times, torch.Tensor):
+            st = spike_times.detach().to(device=dev, dtype=_F64).contiguous()
+        else:
+            st = torch.from_numpy(np.ascontiguousarray(np.asarray(spike_times)).astype(np.float64)).to(dev)
+        self._S = int(st.numel())
+        self._seg_off, self._spike_t, self._spike_cnt = seg.contiguous(), st.reshape(-1), cnt.contiguous()
+        self._spike_R, self._spike_N = int(R), int(N)
+        self._spikes_set = True
+        self._ready = False
+        self._spike_key = None
+
+    def setELLCalculationParams(self, eLLCalculationParams):
+        self._tq = self._to_dev(eLLCalculationParams["leg_quad_points"]).reshape(
+            eLLCalculationParams["leg_quad_points"].shape[0], -1).contiguous()
+        self._wq = self._to_dev(eLLCalculationParams["leg_quad_weights"]).reshape(self._tq.shape).contiguous()
+        self._Q = int(self._tq.shape[1])
+        self._quad_set = True
+        self._ready = False
+
+    def setPriorCovRegParam(self, priorCovRegParam):
+        self._reg = float(priorCovRegParam)
+        self._kzz_key = None
+
+    def setParamsAndData(self, measurements, initial_params, eLLCalculationParams, priorCovRegParam):
+        self.setMeasurements(measurements=measurements)
+        self.setInitialParams(initial_params=initial_params)
+        self.setELLCalculationParams(eLLCalculationParams=eLLCalculationParams)
+        self.setPriorCovRegParam(priorCovRegParam=priorCovRegParam)
+        self.buildKernelsMatrices()
+
+    # ------------------------------------------------------------------ getters (svLowerBound.py:101-114)
+    def getSVPosteriorOnIndPointsParams(self):
+        return list(self._m) + list(self._cv)
+
+    def getSVEmbeddingParams(self):
+        return [self._C, self._d]
+
+    def getKernels(self):
+        return self._kernels
+
+    def getKernelsParams(self):
+        return list(self._theta)
+
+    def getIndPointsLocs(self):
+        return list(self._Z)
+
+    # ------------------------------------------------------------------ buffers
+    def _prepare(self):
+        if self._ready:
+            return
+        if not (self._params_set and self._spikes_set and self._quad_set and self._reg is not None):
+            raise RuntimeError("model is not fully specified: call setKernels, setInitialParams, "
+                               "setMeasurements, setELLCalculationParams and setPriorCovRegParam first")
+        R, N, K, Q = self._R, self._N, self._K, self._Q
+        if self._spike_R != R or self._spike_N != N:
+            raise ValueError(f"measurements are ({self._spike_R} trials, {self._spike_N} neurons) "
+                             f"but parameters are ({R}, {N})")
+        if self._tq.shape[0] != R:
+            raise ValueError("leg_quad_points must have one row per trial")
+        _cabi.lib()
+        dev = self._dev()
+        e = lambda *shape: torch.empty(*shape, dtype=_F64, device=dev)
+        n_ntiles = (N + _cabi.EMBED_TN - 1) // _cabi.EMBED_TN
+        self._n_ntiles = n_ntiles
+        ws = dict(
+            L=e(R * self._MM), Li=e(R * self._MM), X=e(R * self._MM), c=e(R * self._KM), alpha=e(R * self._KM),
+            logdetL=e(R * K), kl_rk=e(R * K), A_q=torch.zeros(R * self._MM, dtype=_F64, device=dev),
+            abar_q=torch.zeros(R * self._KM, dtype=_F64, device=dev),
+            abar_spk=torch.zeros(R * self._KM, dtype=_F64, device=dev),
+            dz_acc=torch.zeros(R * self._KM, dtype=_F64, device=dev),
+            dth_part=torch.zeros(R * self._TH, dtype=_F64, device=dev),
+            mu_q=e(R * Q * K), var_q=e(R * Q * K), mubar_part=e(n_ntiles * R * Q * K),
+            varbar_part=e(n_ntiles * R * Q * K),
+            term1_part=torch.zeros(_cabi.TERM1_SLOTS, dtype=_F64, device=dev),
+            info=torch.zeros(4, dtype=torch.int32, device=dev))
+        self._ws = ws
+        self._shared_len = _cabi.SHARED_HDR + N * K + N + self._TH
+        dims = _cabi.Dims(R=R, N=N, K=K, Q=Q, KM=self._KM, MM=self._MM, PP=self._PP, TH=self._TH,
+                          Mmax=max(self._M), n_ntiles=n_ntiles, S=self._S, reg=self._reg,
+                          desc_host=ctypes.cast(self._desc_host, ctypes.POINTER(_cabi.LatentDesc)))
+        self._dims = dims
+        b = _cabi.Buffers()
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        b.desc, b.kscale, b.theta = ptr(self._desc_dev), ptr(self._kscale), ptr(self._thbuf)
+        b.Z, b.m, b.cholvec = ptr(self._Zbuf), ptr(self._mbuf), ptr(self._cvbuf)
+        b.C, b.d, b.tq, b.wq = ptr(self._C), ptr(self._d), ptr(self._tq), ptr(self._wq)
+        b.spike_t, b.seg_off, b.spike_cnt = ptr(self._spike_t), ptr(self._seg_off), ptr(self._spike_cnt)
+        for name, t in ws.items():
+            setattr(b, name, ptr(t))
+        b.mu_s = None
+        self._bufs = b
+        self._ready = True
+        self._kzz_key = self._spike_key = None
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self._dev()).cuda_stream)
+
+    def _param_versions(self):
+        return (self._Zbuf._version, self._thbuf._version, self._reg)
+
+    # ------------------------------------------------------------------ the hot path
+    def buildKernelsMatrices(self):
+        """Reference semantics (svLowerBound.py:77-78): everything derived from (theta, Z) is
+        recomputed from their current values at the next evaluation."""
+        self._kzz_key = None
+        self._spike_key = None
+
+    def _run(self, flags):
+        """One fused value+gradient pass (svgpfa_elbo_grad).  Returns (shared, gZ, gm, gcholvec)."""
+        self._prepare()
+        dev = self._dev()
+        R = self._R
+        kz_key = self._param_versions()
+        sp_key = kz_key + (self._C._version,)
+        call_flags = flags
+        if self._kzz_key == kz_key:
+            call_flags |= _cabi.REUSE_KZZ
+        if self._spike_key == sp_key and not (flags & (_cabi.GRAD_KERNEL | _cabi.GRAD_INDLOCS | _cabi.GRAD_EMBEDDING)):
+            call_flags |= _cabi.REUSE_SPIKE
+        b = self._bufs
+        shared = torch.empty(self._shared_len, dtype=_F64, device=dev)
+        b.shared = shared.data_ptr()
+        gZ = gm = gcv = None
+        if flags & _cabi.GRAD_INDLOCS:
+            gZ = torch.empty(R * self._KM, dtype=_F64, device=dev)
+            b.gZ = gZ.data_ptr()
+        if flags & _cabi.GRAD_POSTERIOR:
+            gm = torch.empty(R * self._KM, dtype=_F64, device=dev)
+            gcv = torch.empty(R * self._PP, dtype=_F64, device=dev)
+            b.gm, b.gcholvec = gm.data_ptr(), gcv.data_ptr()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().svgpfa_elbo_grad(ctypes.byref(self._dims), ctypes.byref(b),
+                                                     call_flags, self._stream()), "elbo_grad")
+        self._kzz_key, self._spike_key = kz_key, sp_key
+        self._finish(shared)
+        return shared, gZ, gm, gcv
+
+    def _finish(self, shared):
+        if self._pg is not None:
+            # the one exchange step of the path: [elbo.. | dC | dd | dtheta] summed over trial shards
+            torch.distributed.all_reduce(shared, group=self._pg)
+        if self._check_errors:
+            host = torch.cat([shared[:1], self._ws["info"].to(_F64)]).cpu()
+            if int(host[1]) == _cabi.INFO_NOT_PD:
+                self._kzz_key = self._spike_key = None
+                raise torch.linalg.LinAlgError(
+                    f"linalg.cholesky: Kzz of trial {int(host[2])}, latent {int(host[3])} is not positive-definite")
+            if math.isinf(float(host[0])):
+                warnings.warn("infinity lower bound detected")       # svLowerBound.py:51-53
+
+    def _leaves(self):
+        return list(self._m) + list(self._cv) + [self._C, self._d] + list(self._theta) + list(self._Z)
+
+    def eval(self):
+        """ELL - KL as a 0-dim float64 tensor, differentiable w.r.t. every leaf that currently has
+        ``requires_grad=True`` (svLowerBound.py:47-54)."""
+        self._prepare()
+        return _LowerBoundFn.apply(self, None, *self._leaves())
+
+    # ------------------------------------------------------------------ embedding M-step (svEM.py:225-232)
+    def computeSVPosteriorOnLatentsStats(self):
+        """Latent posterior statistics at quadrature points (mean, var: (R,Q,K)) and at spike times
+        (mean only: the exponential link never reads the variance).  Layout follows
+        expectedLogLikelihood.py:141-147; the per-trial spike tensors are views of one (S,K) buffer."""
+        self._prepare()
+        dev = self._dev()
+        b, lib = self._bufs, _cabi.lib()
+        kz_key = self._param_versions()
+        with torch.cuda.device(dev):
+            if self._kzz_key != kz_key:
+                self._ws["info"].zero_()
+                _cabi.check(lib.svgpfa_kzz_chol_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+                self._kzz_key = kz_key
+            _cabi.check(lib.svgpfa_indpoints_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+            _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+            mu_s = torch.empty(max(self._S, 1) * self._K, dtype=_F64, device=dev)
+            b.mu_s = mu_s.data_ptr()
+            _cabi.check(lib.svgpfa_spike_latent_means(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+        R, Q, K = self._R, self._Q, self._K
+        mu_q = self._ws["mu_q"].view(R, Q, K).clone()
+        var_q = self._ws["var_q"].view(R, Q, K).clone()
+        mu_s = mu_s[:self._S * K].view(self._S, K)
+        off = self._seg_off[::self._N].cpu().tolist() if self._N else [0] * (R + 1)
+        means = [mu_s[off[r]:off[r + 1]] for r in range(R)]
+        if self._check_errors and int(self._ws["info"][0].item()) == _cabi.INFO_NOT_PD:
+            raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
+        return {"allTimes": (mu_q, var_q), "assocTimes": (means, [None] * R), "_b200_mu_s": mu_s}
+
+    def evalELLSumAcrossTrialsAndNeurons(self, svPosteriorOnLatentsStats=None):
+        """Expected log-likelihood only (no KL).  With cached statistics it is a function of (C, d)
+        alone (svLowerBound.py:72-75)."""
+        self._prepare()
+        if svPosteriorOnLatentsStats is None:
+            svPosteriorOnLatentsStats = self.computeSVPosteriorOnLatentsStats()
+        return _LowerBoundFn.apply(self, svPosteriorOnLatentsStats, *self._leaves())
+
+    def _run_cached(self, stats):
+        dev = self._dev()
+        mu_q, var_q = stats["allTimes"]
+        mu_s = stats.get("_b200_mu_s")
+        if mu_s is None:
+            mu_s = torch.cat([self._to_dev(x) for x in stats["assocTimes"][0]], 0)
+        mu_q = self._to_dev(mu_q).contiguous()
+        var_q = self._to_dev(var_q).contiguous()
+        mu_s = self._to_dev(mu_s).contiguous()
+        b = _cabi.Buffers.from_buffer_copy(self._bufs)
+        shared = torch.empty(self._shared_len, dtype=_F64, device=dev)
+        b.shared, b.mu_q, b.var_q, b.mu_s = shared.data_ptr(), mu_q.data_ptr(), var_q.data_ptr(), mu_s.data_ptr()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().svgpfa_cached_ell_fwd_bwd(ctypes.byref(self._dims), ctypes.byref(b),
+                                                              self._stream()), "cached_ell_fwd_bwd")
+        if self._pg is not None:
+            torch.distributed.all_reduce(shared, group=self._pg)
+        self._cached_keepalive = (mu_q, var_q, mu_s)
+        return shared
+
+    # ------------------------------------------------------------------ post-fit read-outs
+    def predictLatents(self, times):
+        """Posterior mean and variance of the latents at ``times`` (R, T, 1)
+        (svPosteriorOnLatents.py:57-77).  Forward-only call of the quadrature kernels."""
+        self._prepare()
+        dev = self._dev()
+        t = self._to_dev(times).reshape(self._R, -1).contiguous()
+        T = int(t.shape[1])
+        mu = torch.empty(self._R * T * self._K, dtype=_F64, device=dev)
+        var = torch.empty_like(mu)
+        dims = _cabi.Dims.from_buffer_copy(self._dims)
+        dims.Q = T
+        b = _cabi.Buffers.from_buffer_copy(self._bufs)
+        b.tq, b.mu_q, b.var_q = t.data_ptr(), mu.data_ptr(), var.data_ptr()
+        lib = _cabi.lib()
+        with torch.cuda.device(dev):
+            if self._kzz_key != self._param_versions():
+                _cabi.check(lib.svgpfa_kzz_chol_fwd(ctypes.byref(self._dims), ctypes.byref(self._bufs), self._stream()))
+                self._kzz_key = self._param_versions()
+            _cabi.check(lib.svgpfa_indpoints_fwd(ctypes.byref(self._dims), ctypes.byref(self._bufs), self._stream()))
+            _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(dims), ctypes.byref(b), self._stream()))
+        return mu.view(self._R, T, self._K), var.view(self._R, T, self._K)
+
+    def predictEmbedding(self, times):
+        """Embedding mean / variance at ``times`` (svEmbedding.py:80-92)."""
+        mu, var = self.predictLatents(times)
+        C, d = self._C.detach(), self._d.detach().reshape(1, 1, -1)
+        return mu @ C.T + d, var @ (C.T ** 2)
+
+    def computeExpectedPosteriorCIFs(self, times):
+        """exp(mean + var/2) per trial and neuron (expectedLogLikelihood.py:62-73)."""
+        e_mean, e_var = self.predictEmbedding(times)
+        cif = torch.exp(e_mean + 0.5 * e_var)
+        return [[cif[r, :, n] for n in range(cif.shape[2])] for r in range(cif.shape[0])]
+
+    # ------------------------------------------------------------------ pickling (svEM.py:89-92,175-181)
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for key in ("_bufs", "_dims", "_desc_host", "_ws", "_cached_keepalive", "_pg"):
+            st.pop(key, None)
+        st["_ready"] = False
+        st["_kzz_key"] = st["_spike_key"] = None
+        st["_desc_rows"] = [tuple(getattr(self._desc_host[k], f) for f, _ in _cabi.LatentDesc._fields_)
+                            for k in range(self._K)] if self._params_set else None
+        return st
+
+    def __setstate__(self, st):
+        rows = st.pop("_desc_rows", None)
+        self.__dict__.update(st)
+        self._pg = None
+        self._bufs = None
+        if rows is not None:
+            desc = (_cabi.LatentDesc * len(rows))()
+            for k, row in enumerate(rows):
+                desc[k] = _cabi.LatentDesc(*row)
+            self._desc_host = desc
+
+
+def buildModelB200(kernels, device=None, process_group=None):
+    """Sibling of ``SVGPFAModelFactory.buildModelPyTorch(kernels=...)`` for the in-scope model
+    (point process, exponential link, linear embedding, Cholesky Kzz solves, Cholesky-vector
+    covariance; stats/svGPFAModelFactory.py:40-148)."""
+    return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group)

@@ -1,6 +1,6 @@
 """Seeded synthetic svGPFA problem instances.
 
-One generator feeds the oracle, the golden-vector script, the parity tests and
+One generator feeds the CPU checker, the golden-vector script, the parity tests and
 ``bench.py`` so that every arm sees the same numbers.  A *case* is a plain dict
 of numpy arrays / python lists with the field names the reference's
 ``initial_params`` dictionary uses (``/root/reference/src/svGPFA/utils/initUtils.py:468-481``):
