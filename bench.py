@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""Benchmark of the svGPFA lower-bound hot path: ELBO+gradient evaluations per second, float64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config config5]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One *step* = one unit of work of SURVEY.md §8d on one batch of synthetic input:
+``model.buildKernelsMatrices(); v = model.eval(); (-v).backward()`` with ``requires_grad=True`` on
+ALL parameter groups.  The workload is BASELINE.json's config #5 (R=20000 trials, N=500, K=20, M=32,
+Q=200; it fits one B200).  With N GPUs the same R trials are sharded over the ranks (strong scaling)
+and the packed [ELBO | dC | dd | dtheta] buffer is all-reduced once per evaluation.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (spike_fwd_bwd): FP64-pipe bound.  achieved = (F_spike + N_exp * c_exp)/t with
+                F_spike, N_exp from SURVEY.md §8d, c_exp = measured DFMA-flops-per-libdevice-exp, t = the
+                kernel's mean device time inside the timed region (CUDA events recorded by the library);
+                peak = DFMA throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  stages_ms     mean device time of every kernel stage inside the timed region
+  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample of the same workload
+  e2e           same metric through the host-buffer C-ABI entry, copies inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "elbo_grad_evals_per_sec"
+UNIT = "evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="config5")
+    ap.add_argument("--trials", type=int, default=None, help="override R (debugging only; marks the line)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from svgpfa_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[args.config])
+    if args.trials is not None:
+        cfg["R"] = args.trials
+    return cfg
+
+
+def config_dict(args, cfg, world):
+    return {"workload": f"{args.config}: synthetic R={cfg['R']} N={cfg['N']} K={cfg['K']} M={cfg['M']} Q={cfg['Q']} "
+                        f"{'mixed ExpQuad/Periodic' if cfg['mixed'] else 'ExponentialQuadratic'} kernels"
+                        f"{', heavy ragged spikes' if cfg['ragged'] else ''}, reg=1e-3",
+            "unit_of_work": "buildKernelsMatrices(); eval(); backward() over all parameter groups",
+            "trials_total": cfg["R"], "trials_per_gpu": -(-cfg["R"] // world), "parallelism": f"trial-shard x{world}",
+            "l2": "inputs larger than L2 (spike times + per-trial parameters re-read every step)",
+            "reduced": args.trials is not None}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_seconds_per_trial(case_np, threads):
+    from oracle import svgpfa_oracle as orc
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    orc.elbo_and_grads(case_np)
+    return time.perf_counter() - t0
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is Python and cannot
+    travel to the GPU box) on the host cores, bounded sample per step, extrapolated linearly in trials (the
+    reference's cost is linear in R: independent trials, python loops -- SURVEY.md §6.2)."""
+    from svgpfa_b200 import synthetic
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    budget = 150.0 / max(1, args.steps + args.warmup)         # seconds of CPU work per step
+    probe = synthetic.make_case(dict(cfg, R=2), seed=0)
+    cpu_seconds_per_trial(probe, threads)                     # warm caches / thread pools
+    per_trial = cpu_seconds_per_trial(probe, threads) / 2.0
+    r_sub = int(max(2, min(cfg["R"], 32, budget / max(per_trial, 1e-6))))
+    case = synthetic.make_case(dict(cfg, R=r_sub), seed=0)
+    from oracle import svgpfa_oracle as orc
+    for _ in range(args.warmup):
+        orc.elbo_and_grads(case)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.elbo_and_grads(case)
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * cfg["R"] / r_sub
+    value = 1.0 / full
+    sample = f"{r_sub} of {cfg['R']} trials per step, time extrapolated linearly to {cfg['R']} trials"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": config_dict(args, cfg, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "cpu": cpu_model_name(), "measured_ms_per_sample_step": dt * 1e3},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measure_peaks(device):
+    """DFMA / libdevice exp / sincospi / library exp throughput of this GPU (per second)."""
+    from svgpfa_b200 import _cabi
+    lib = _cabi.lib()
+    nsm = torch.cuda.get_device_properties(device).multi_processor_count
+    blocks = nsm * 8
+    out = torch.empty(blocks * 256, dtype=torch.float64, device=device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    res = {}
+    for kind, name, iters in ((0, "dfma", 20000), (1, "exp", 2000), (2, "sincospi", 1000), (3, "exp_lib", 2000)):
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _cabi.check(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), stream))
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        res[name] = blocks * 256 * iters * 8 / (best * 1e-3)
+    return res
+
+
+def algorithmic_counts(cfg, R, S):
+    """SURVEY.md §8d per-unit work formulas for R trials holding S spikes."""
+    N, K, M, Q = cfg["N"], cfg["K"], cfg["M"], cfg["Q"]
+    n_per = sum(1 for k in range(K) if cfg["mixed"] and k % 2 == 1)
+    return {
+        "F_setup": R * K * (2 * M ** 3 + 6 * M ** 2),
+        "F_quad": R * K * Q * (6 * M ** 2 + 18 * M),
+        "F_embed": R * Q * (12 * N * K + 3 * N),
+        "F_spike": S * K * 10 * M + S * 4 * K,
+        "N_exp_spike": S * K * M,
+        "N_sin_spike": S * n_per * M,
+        "N_exp_other": R * K * M * (M + 1) // 2 + R * K * Q * M + R * Q * N,
+        "bytes_min": 8 * (2 * R * K * (2 * M + M * (M + 1) // 2) + 2 * R * Q) + 12 * S,
+    }
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from svgpfa_b200 import _cabi, synthetic
+    from svgpfa_b200.testing import model_from_case, set_requires_grad
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    cfg = workload(args)
+    R = cfg["R"]
+    # contiguous trial blocks (uniform-rate workloads: equal trial counts balance the spikes)
+    r0, r1 = (R * rank) // world, (R * (rank + 1)) // world
+    case = synthetic.make_case_torch(cfg, device, seed=0, r0=r0, r1=r1)
+    S_local = int(case["spike_times"].numel())
+    model = model_from_case(case, device=device, process_group=pg)
+    set_requires_grad(model)
+    leaves = model._leaves()
+    lib = _cabi.lib()
+
+    def step():
+        for p in leaves:
+            p.grad = None
+        model.buildKernelsMatrices()
+        v = model.eval()
+        (-v).backward()
+        return v
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(3, args.warmup)):
+        v = step()
+    elbo = float(v.item())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    # ---- timed region: K steps, device time, stage events recorded by the library
+    n_ev = len(_cabi.STAGES) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    for row in evs:                       # events are created lazily: record once so that the handles exist
+        for e in row:
+            e.record()
+    ev_arr = [(ctypes.c_void_p * n_ev)(*[e.cuda_event for e in row]) for row in evs]
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    start.record()
+    for i in range(args.steps):
+        lib.svgpfa_set_stage_events(ev_arr[i])
+        step()
+    lib.svgpfa_set_stage_events(None)
+    stop.record()
+    barrier()
+    wall1 = time.time()
+    ms_total = start.elapsed_time(stop)
+    stage_ms = np.zeros(len(_cabi.STAGES))
+    for row in evs:
+        for j in range(len(_cabi.STAGES)):
+            stage_ms[j] += row[j].elapsed_time(row[j + 1])
+    stage_ms /= args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    st = torch.tensor(stage_ms, dtype=torch.float64, device=device)
+    tot_S = torch.tensor([float(S_local)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_S, op=dist.ReduceOp.SUM)
+    ms_step = float(t.item()) / args.steps
+    value = 1e3 / ms_step
+    clocks = sampler.summary(wall0, wall1) if rank == 0 else None
+    if rank == 0:
+        sampler.stop()
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        io = model.makeHostIO(pin=True)
+        for _ in range(2):
+            model.evalAndGradHost(io, copy_static=True)
+        barrier()
+        t0 = time.perf_counter()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            elbo_h, h2d, d2h = model.evalAndGradHost(io, copy_static=True)
+            if world > 1:
+                sh = io["shared"].to(device, non_blocking=True)
+                dist.all_reduce(sh)
+                io["shared"].copy_(sh)
+        e_stop.record()
+        barrier()
+        ms_e2e = e_start.elapsed_time(e_stop) / n_e2e
+        wall_e2e = (time.perf_counter() - t0) / n_e2e * 1e3
+        # parameters-only variant (spikes resident, as in an optimiser loop)
+        e_start.record()
+        for _ in range(n_e2e):
+            _, h2d_p, d2h_p = model.evalAndGradHost(io, copy_static=False)
+        e_stop.record()
+        barrier()
+        ms_e2e_p = e_start.elapsed_time(e_stop) / n_e2e
+        te = torch.tensor([ms_e2e, ms_e2e_p, float(h2d), float(d2h), float(h2d_p)], dtype=torch.float64, device=device)
+        if world > 1:
+            mx = te.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = te.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            te = torch.stack([mx[0], mx[1], sm[2], sm[3], sm[4]])
+        e2e = {"value": 1e3 / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(te[2]),
+               "d2h_bytes_per_step": int(te[3]), "ms_per_step": float(te[0]), "wall_ms_per_step_rank0": wall_e2e,
+               "params_only": {"value": 1e3 / float(te[1]), "h2d_bytes_per_step": int(te[4])},
+               "api": "svgpfa_elbo_grad_host (pinned host buffers; spikes, quadrature and parameters copied every step)"}
+        del io
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = measure_peaks(device)
+    cnt = algorithmic_counts(cfg, r1 - r0, S_local)
+    c_exp = 2.0 * peaks["dfma"] / peaks["exp"]           # DFMA-flops one libdevice exp is worth
+    c_sin = 2.0 * peaks["dfma"] / peaks["sincospi"]
+    spike_idx = _cabi.STAGES.index("spike_fwd_bwd")
+    t_spike = float(st[spike_idx]) * 1e-3
+    flops_equiv = cnt["F_spike"] + cnt["N_exp_spike"] * c_exp + cnt["N_sin_spike"] * c_sin
+    peak_tf = 2.0 * peaks["dfma"] / 1e12
+    achieved = flops_equiv / t_spike / 1e12
+    roofline = {"bound": "fp64", "kernel": "spike_fwd_bwd_kernel", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": "DFMA throughput measured in this run (svgpfa_peak_probe); MEASURED_PEAKS.json has "
+                               "no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
+                "algorithmic": {"flops": cnt["F_spike"], "exp": cnt["N_exp_spike"], "sincospi": cnt["N_sin_spike"],
+                                "flops_per_exp": c_exp, "flops_per_sincospi": c_sin},
+                "share_of_step": t_spike * 1e3 / float(st.sum()),
+                "launch_ms": t_spike * 1e3}
+    total_equiv = (cnt["F_setup"] + cnt["F_quad"] + cnt["F_embed"] + cnt["F_spike"]
+                   + (cnt["N_exp_spike"] + cnt["N_exp_other"]) * c_exp + cnt["N_sin_spike"] * c_sin)
+    roofline["whole_step_frac"] = total_equiv / (ms_step * 1e-3) / 1e12 / peak_tf
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        threads = os.cpu_count() or 1
+        probe = synthetic.case_to_numpy(case, 0, 2)
+        cpu_seconds_per_trial(probe, threads)
+        per_trial = cpu_seconds_per_trial(probe, threads) / 2.0
+        r_sub = int(max(2, min(r1 - r0, 32, args.cpu_seconds / max(per_trial, 1e-6))))
+        sample = synthetic.case_to_numpy(case, 0, r_sub)
+        from oracle import svgpfa_oracle as orc
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        ref = orc.elbo_and_grads(sample)
+        dt = time.perf_counter() - t0
+        full = dt * R / r_sub
+        cpu = {"value": 1.0 / full, "unit": UNIT, "cores": threads, "kind": "port", "cpu": cpu_model_name(),
+               "sample": f"first {r_sub} of {R} trials, one evaluation, time extrapolated linearly to {R} trials",
+               "measured_s_on_sample": dt}
+        # parity of the timed configuration on that sample (same inputs, GPU path vs oracle)
+        sub = model_from_case(synthetic.case_to_numpy(case, 0, r_sub), device=device)
+        set_requires_grad(sub)
+        vs = sub.eval()
+        vs.backward()
+        cpu["parity_elbo_rel_err"] = abs(vs.item() - ref["elbo"]) / abs(ref["elbo"])
+        gC = sub.getSVEmbeddingParams()[0].grad.cpu().numpy()
+        cpu["parity_gradC_rel_err"] = float(np.linalg.norm(gC - ref["grad_C"]) / np.linalg.norm(ref["grad_C"]))
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "b200",
+            "config": config_dict(args, cfg, world), "elbo": elbo, "spikes_total": int(tot_S.item()),
+            "clocks": clocks, "gpu_launches": 9 * args.steps,
+            "stages_ms": {n: float(x) for n, x in zip(_cabi.STAGES, st.tolist())},
+            "roofline": roofline, "peaks_measured": {k: float(v) for k, v in peaks.items()}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

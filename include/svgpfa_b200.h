@@ -212,6 +212,24 @@ typedef struct svgpfa_host_io {
 int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                           uint32_t flags, void* stream);
 
+/* Measurement hooks (bench.py only).
+ * svgpfa_set_stage_events: when `events` is non-NULL the next svgpfa_elbo_grad calls on this host thread
+ *   record events[0] before the first stage and events[i+1] after stage i (stages in the order of
+ *   SVGPFA_STAGE_*; a skipped stage records its event immediately), so that a caller can read every
+ *   kernel's device time inside its own timed region.  `events` = SVGPFA_N_STAGES+1 cudaEvent_t handles.
+ *   Pass NULL to switch recording off.
+ * svgpfa_peak_probe: FP64 pipe micro-benchmarks used as roofline denominators (SURVEY.md §8d asks the
+ *   builder to MEASURE pi_fma / pi_exp / pi_sin).  kind 0: dependent-chain-free DFMA, 1: libdevice exp,
+ *   2: libdevice sincospi, 3: this library's exp (svgpfa_exp_neg).  Launches `blocks` x 256 threads, each
+ *   doing `iters` x 8 operations; the caller times it with events.  out: `blocks*256` doubles (sink). */
+enum { SVGPFA_STAGE_KZZ_CHOL = 0, SVGPFA_STAGE_INDPOINTS_FWD, SVGPFA_STAGE_QUAD_LATENT_FWD, SVGPFA_STAGE_QUAD_EMBED,
+       SVGPFA_STAGE_QUAD_LATENT_BWD, SVGPFA_STAGE_SPIKE, SVGPFA_STAGE_INDPOINTS_BWD, SVGPFA_STAGE_FINALIZE,
+       SVGPFA_N_STAGES };
+int svgpfa_set_stage_events(void** events);
+int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, void* stream);
+/* Test hook: y_fast[i] = the library's exp for non-positive arguments, y_ref[i] = libdevice exp(x[i]). */
+int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

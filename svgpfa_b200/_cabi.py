@@ -70,7 +70,12 @@ SYMBOLS = {
     "svgpfa_cached_ell_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_build_segments_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgpfa_elbo_grad_host": (C.c_int, [_P(Dims), _P(Buffers), _P(HostIO), C.c_uint32, C.c_void_p]),
+    "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),
+    "svgpfa_peak_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "svgpfa_exp_neg_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
+STAGES = ("kzz_chol", "indpoints_fwd", "quad_latent_fwd", "quad_embed", "quad_latent_bwd", "spike_fwd_bwd",
+          "indpoints_bwd", "finalize")
 
 _lib = None
 

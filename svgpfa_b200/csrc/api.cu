@@ -10,6 +10,49 @@ int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* bu
 namespace {
 
 thread_local char g_err[256] = "";
+thread_local cudaEvent_t* g_stage_events = nullptr;
+
+inline void stage_mark(int idx, cudaStream_t st) {
+    if (g_stage_events) cudaEventRecord(g_stage_events[idx], st);
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 pipe probes
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out) {
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab(etab);
+    __syncthreads();
+    const double seed = 1e-3 * (threadIdx.x + 1) + 1e-7 * blockIdx.x;
+    double a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = seed + 0.01 * e;
+    const double m = 0.999999, c = 1e-9;
+    for (long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (KIND == 0) a[e] = fma(a[e], m, c);
+            else if (KIND == 1) a[e] = exp(-a[e] * 0.5) + c;           // 1 mul + 1 add + exp
+            else if (KIND == 2) { double s, cs; sincospi(a[e], &s, &cs); a[e] = s * cs + 0.25; }
+            else a[e] = svgpfa_exp_neg(-a[e] * 0.5, etab) + c;
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += a[e];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n) {
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab(etab);
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        yf[i] = svgpfa_exp_neg(x[i], etab);
+        yr[i] = exp(x[i]);
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // reductions into `shared`
@@ -79,7 +122,34 @@ int svgpfa_set_error(int code, const char* where, cudaError_t ce) {
 }
 
 extern "C" int svgpfa_abi_version(void) { return SVGPFA_ABI_VERSION; }
+
+extern "C" int svgpfa_set_stage_events(void** events) {
+    g_stage_events = reinterpret_cast<cudaEvent_t*>(events);
+    return SVGPFA_OK;
+}
+
+extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, void* stream) {
+    if (!out || blocks < 1 || iters < 0) return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+        case 0: peak_probe_kernel<0><<<blocks, 256, 0, st>>>((long)iters, out); break;
+        case 1: peak_probe_kernel<1><<<blocks, 256, 0, st>>>((long)iters, out); break;
+        case 2: peak_probe_kernel<2><<<blocks, 256, 0, st>>>((long)iters, out); break;
+        case 3: peak_probe_kernel<3><<<blocks, 256, 0, st>>>((long)iters, out); break;
+        default: return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe kind", cudaSuccess);
+    }
+    SVGPFA_CHECK_LAUNCH("peak_probe");
+    return SVGPFA_OK;
+}
 extern "C" const char* svgpfa_last_error(void) { return g_err; }
+
+extern "C" int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream) {
+    if (!x || !y_fast || !y_ref || n < 0) return svgpfa_set_error(SVGPFA_E_ARG, "exp_neg_eval", cudaSuccess);
+    if (n == 0) return SVGPFA_OK;
+    exp_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(x, y_fast, y_ref, (long)n);
+    SVGPFA_CHECK_LAUNCH("exp_neg_eval");
+    return SVGPFA_OK;
+}
 
 extern "C" int svgpfa_finalize(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     int rc = check_dims(dims, buf, "finalize");
@@ -111,14 +181,24 @@ extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* b
         cudaMemsetAsync(buf->dz_acc, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
         cudaMemsetAsync(buf->dth_part, 0, sizeof(double) * (size_t)dims->R * dims->TH, st);
     }
+    stage_mark(0, st);
     if (!(flags & SVGPFA_REUSE_KZZ)) { rc = svgpfa_kzz_chol_fwd(dims, buf, stream); if (rc) return rc; }
+    stage_mark(1 + SVGPFA_STAGE_KZZ_CHOL, st);
     rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc;
+    stage_mark(1 + SVGPFA_STAGE_INDPOINTS_FWD, st);
     rc = svgpfa_quad_latent_fwd(dims, buf, stream); if (rc) return rc;
+    stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_FWD, st);
     rc = svgpfa_quad_embed_fwd_bwd(dims, buf, flags, stream); if (rc) return rc;
+    stage_mark(1 + SVGPFA_STAGE_QUAD_EMBED, st);
     if (flags & lat) { rc = svgpfa_quad_latent_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_BWD, st);
     if (!reuse_spike) { rc = svgpfa_spike_fwd_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    stage_mark(1 + SVGPFA_STAGE_SPIKE, st);
     if (flags & lat) { rc = svgpfa_indpoints_bwd(dims, buf, flags, stream); if (rc) return rc; }
-    return svgpfa_finalize(dims, buf, flags, stream);
+    stage_mark(1 + SVGPFA_STAGE_INDPOINTS_BWD, st);
+    rc = svgpfa_finalize(dims, buf, flags, stream);
+    stage_mark(1 + SVGPFA_STAGE_FINALIZE, st);
+    return rc;
 }
 
 extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {

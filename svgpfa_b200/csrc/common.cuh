@@ -6,7 +6,36 @@
 
 #include "svgpfa_b200.h"
 
+#include "exp_table.cuh"
+
 #define SVGPFA_PI 3.14159265358979323846
+
+// exp(x) for x <= 0 -- every covariance-kernel value is exp of a non-positive number.
+// 64-entry table 2^(j/64) (`tab`, SHARED memory) + degree-5 polynomial on |r| <= ln2/128:
+// 11 FP64-pipe operations instead of libdevice's ~17 + special-case branches; relative error < 3e-16
+// (tests/test_gpu_kernels.py::test_exp_neg_accuracy).  Results below 2^-1021 are flushed to zero.
+__device__ __forceinline__ void svgpfa_load_exp_tab(double* tab) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = svgpfa_exp2_tab_g[i];
+}
+
+__device__ __forceinline__ double svgpfa_exp_neg(double x, const double* __restrict__ tab) {
+    x = fmax(x, -745.0);
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest-integer trick
+    const double t = fma(x, SVGPFA_EXP_INV_L, MAGIC);
+    const double nd = t - MAGIC;
+    const int n = __double2loint(t);
+    double r = fma(nd, -SVGPFA_EXP_L_HI, x);
+    r = fma(nd, -SVGPFA_EXP_L_LO, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double T = tab[n & 63];
+    const double e = fma(T * r, q, T);                        // T * exp(r)
+    const int m = n >> 6;
+    const double scaled = __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));
+    return (m < -1021) ? 0.0 : scaled;
+}
 
 // Per-latent kernel constants derived from theta (kernels.py:33-46, 73-85).
 //   expquad : kappa = s2 exp(nh d^2),            nh = -0.5 / l^2

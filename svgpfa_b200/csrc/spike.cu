@@ -32,6 +32,9 @@ __device__ __forceinline__ double seg_sum(double v, unsigned same_mask) {
 template <bool KGRAD>
 __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
                                                                     int n_chunks, int chunk) {
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab(etab);
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x / n_chunks, nc = blockIdx.x - r * n_chunks;
     const int grp = blockIdx.y * SP_WPB + warp;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims 
             for (int64_t s = s0; s < s1; ++s) {
                 const double dl = st[s] - z;
                 const double q = dl * dl;
-                const double kv = exp(kc.nh * q);
+                const double kv = svgpfa_exp_neg(kc.nh * q, etab);
                 pn += kv;
                 if (KGRAD) {
                     const double t = kv * dl;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims 
                 double sn, cs;
                 sincospi(dl * kc.invp, &sn, &cs);
                 const double q = sn * sn;
-                const double kv = exp(kc.nh * q);
+                const double kv = svgpfa_exp_neg(kc.nh * q, etab);
                 pn += kv;
                 if (KGRAD) {
                     const double t = kv * (2.0 * sn * cs);

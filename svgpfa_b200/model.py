@@ -392,6 +392,56 @@ class B200SVLowerBound:
         self._prepare()
         return _LowerBoundFn.apply(self, None, *self._leaves())
 
+    # ------------------------------------------------------------------ host-buffer entry (bench.py "e2e")
+    def makeHostIO(self, pin=True):
+        """Host mirrors (pinned by default) of every input and output of ``svgpfa_elbo_grad_host``,
+        initialised from the current device state."""
+        self._prepare()
+        h = lambda t: (t.detach().cpu().pin_memory() if pin else t.detach().cpu())
+        z = lambda n, dt=_F64: (torch.zeros(n, dtype=dt).pin_memory() if pin else torch.zeros(n, dtype=dt))
+        R = self._R
+        return dict(theta=h(self._thbuf), Z=h(self._Zbuf), m=h(self._mbuf), cholvec=h(self._cvbuf),
+                    C=h(self._C), d=h(self._d), tq=h(self._tq), wq=h(self._wq), spike_t=h(self._spike_t),
+                    seg_off=h(self._seg_off), spike_cnt=h(self._spike_cnt),
+                    shared=z(self._shared_len), gZ=z(R * self._KM), gm=z(R * self._KM), gcholvec=z(R * self._PP),
+                    info=z(4, torch.int32))
+
+    def evalAndGradHost(self, io, flags=_cabi.GRAD_ALL, copy_static=True):
+        """One unit of work through the C ABI with HOST buffers: host->device copies of the inputs,
+        ``svgpfa_elbo_grad``, device->host copies of the bound and the gradients, all on the current
+        stream; returns after the stream has drained.  Returns (elbo, h2d_bytes, d2h_bytes)."""
+        self._prepare()
+        dev = self._dev()
+        R = self._R
+        b = _cabi.Buffers.from_buffer_copy(self._bufs)
+        shared = torch.empty(self._shared_len, dtype=_F64, device=dev)
+        gZ = torch.empty(R * self._KM, dtype=_F64, device=dev)
+        gm = torch.empty(R * self._KM, dtype=_F64, device=dev)
+        gcv = torch.empty(R * self._PP, dtype=_F64, device=dev)
+        b.shared, b.gZ, b.gm, b.gcholvec = shared.data_ptr(), gZ.data_ptr(), gm.data_ptr(), gcv.data_ptr()
+        hio = _cabi.HostIO()
+        for name in ("theta", "Z", "m", "cholvec", "C", "d", "tq", "wq", "spike_t", "seg_off", "spike_cnt",
+                     "shared", "gZ", "gm", "gcholvec", "info"):
+            setattr(hio, name + "_host", io[name].data_ptr())
+        hio.copy_static = 1 if copy_static else 0
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().svgpfa_elbo_grad_host(ctypes.byref(self._dims), ctypes.byref(b), ctypes.byref(hio),
+                                                          flags, self._stream()), "elbo_grad_host")
+            torch.cuda.current_stream(dev).synchronize()
+        self._kzz_key = self._spike_key = None
+        nb = lambda *names: sum(io[n].numel() * io[n].element_size() for n in names)
+        h2d = nb("theta", "Z", "m", "cholvec", "C", "d")
+        if copy_static:
+            h2d += nb("tq", "wq", "spike_t", "seg_off", "spike_cnt")
+        d2h = nb("shared", "info")
+        if flags & _cabi.GRAD_INDLOCS:
+            d2h += nb("gZ")
+        if flags & _cabi.GRAD_POSTERIOR:
+            d2h += nb("gm", "gcholvec")
+        if int(io["info"][0]) == _cabi.INFO_NOT_PD:
+            raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
+        return float(io["shared"][0]), h2d, d2h
+
     # ------------------------------------------------------------------ embedding M-step (svEM.py:225-232)
     def computeSVPosteriorOnLatentsStats(self):
         """Latent posterior statistics at quadrature points (mean, var: (R,Q,K)) and at spike times

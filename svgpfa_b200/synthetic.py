@@ -167,3 +167,80 @@ def load_case(path):
     case["reg"] = float(z["reg"])
     extra = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
     return case, extra
+
+
+def make_case_torch(cfg, device, *, seed=0, reg=1e-3, r0=0, r1=None, T=1.0):
+    """Device-side generator for the large benchmark workloads (same distributions as
+    ``make_case``; different random stream).  Generates trials [r0, r1) of the configuration so
+    that every rank of a trial-sharded run builds only its own shard; the shared parameters
+    (C, d, theta, per-neuron rates) depend on ``seed`` alone.  Returns a case dict of torch tensors
+    on ``device`` (spike_times float64 (S,), spike_counts int64 (R_local, N))."""
+    import torch
+    cfg = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+    R, N, K, M, Q = cfg["R"], cfg["N"], cfg["K"], cfg["M"], cfg["Q"]
+    r1 = R if r1 is None else r1
+    Rl = r1 - r0
+    shared = np.random.default_rng(seed)
+    if cfg["ragged"]:
+        rate = np.exp(shared.uniform(np.log(1.0), np.log(200.0), size=N))
+        d = np.log(shared.uniform(5.0, 35.0, size=N)) + 0.1 * shared.standard_normal(N)
+    else:
+        rate = shared.uniform(5.0, 35.0, size=N)
+        d = np.log(rate) + 0.1 * shared.standard_normal(N)
+    C = 0.3 * shared.standard_normal((N, K))
+    f64 = dict(dtype=torch.float64, device=device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 1000003 + 17 * r0 + 1)
+    kernel_types, kernel_params, Z, m, chol_vecs = [], [], [], [], []
+    for k in range(K):
+        if cfg["mixed"] and (k % 2 == 1):
+            kernel_types.append("periodic")
+            kernel_params.append(torch.tensor([1.0 + 0.1 * k, 0.5 + 0.05 * k], **f64))
+        else:
+            kernel_types.append("expquad")
+            kernel_params.append(torch.tensor([0.1 + 0.05 * k], **f64))
+        base = torch.linspace(0.0, T, M, **f64)
+        jit = (torch.rand(Rl, M, generator=gen, **f64) * 0.2 - 0.1) * T / M
+        Z.append((base[None, :] + jit)[:, :, None].contiguous())
+        m.append(torch.randn(Rl, M, 1, generator=gen, **f64))
+        P = tril_size(M)
+        rows, cols = np.tril_indices(M)
+        diag = torch.tensor((rows == cols).astype(np.float64), **f64)
+        chol_vecs.append((0.1 * diag[None, :] + 0.01 * torch.randn(Rl, P, generator=gen, **f64))[:, :, None].contiguous())
+    x, w = leg_quad(Q, 0.0, T)
+    tq = torch.tensor(x, **f64)[None, :, None].repeat(Rl, 1, 1)
+    wq = torch.tensor(w, **f64)[None, :, None].repeat(Rl, 1, 1)
+    rate_t = torch.tensor(rate, **f64)
+    if cfg["ragged"]:
+        g_r = torch.exp(0.5 * torch.randn(Rl, generator=gen, **f64))
+    else:
+        g_r = torch.ones(Rl, **f64)
+    counts = torch.poisson(g_r[:, None] * rate_t[None, :] * T, generator=gen).to(torch.int64)
+    S = int(counts.sum().item())
+    seg = torch.repeat_interleave(torch.arange(Rl * N, device=device), counts.reshape(-1), output_size=S)
+    key = seg.to(torch.float64) + torch.rand(S, generator=gen, **f64).clamp_(max=1.0 - 1e-9)
+    del seg
+    key, _ = torch.sort(key)
+    times = (key - torch.floor(key)) * T
+    return dict(kernel_types=kernel_types, kernel_params=kernel_params, Z=Z, m=m, chol_vecs=chol_vecs,
+                C=torch.tensor(C, **f64), d=torch.tensor(d, **f64)[:, None].contiguous(),
+                leg_quad_points=tq, leg_quad_weights=wq, spike_times=times, spike_counts=counts,
+                reg=float(reg), T=float(T))
+
+
+def case_to_numpy(case, r0=0, r1=None):
+    """Host copy of trials [r0, r1) of a (torch or numpy) case -- the bounded CPU-baseline sample."""
+    import torch
+    to = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    counts = to(case["spike_counts"])
+    r1 = counts.shape[0] if r1 is None else r1
+    off = np.concatenate([[0], np.cumsum(counts.sum(axis=1))])
+    out = dict(kernel_types=list(case["kernel_types"]), kernel_params=[to(a) for a in case["kernel_params"]],
+               C=to(case["C"]), d=to(case["d"]), reg=case["reg"])
+    for key in ("Z", "m", "chol_vecs"):
+        out[key] = [to(a[r0:r1]) for a in case[key]]
+    for key in ("leg_quad_points", "leg_quad_weights"):
+        out[key] = to(case[key][r0:r1])
+    out["spike_counts"] = counts[r0:r1]
+    out["spike_times"] = to(case["spike_times"][int(off[r0]):int(off[r1])])
+    return out

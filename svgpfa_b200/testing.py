@@ -10,7 +10,8 @@ from .synthetic import nested_spikes
 
 
 def initial_params_from_case(case, device=None):
-    t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device=device)
+    t = lambda a: (a.detach().to(dtype=torch.float64) if isinstance(a, torch.Tensor)
+                   else torch.tensor(np.asarray(a), dtype=torch.float64, device=device))
     return {
         "posterior_on_latents": {
             "posterior_on_ind_points": {"mean": [t(a) for a in case["m"]],
@@ -32,8 +33,9 @@ def model_from_case(case, device=None, process_group=None, nested=False, check_e
         model.setMeasurements(nested_spikes(case))
     else:
         model.setMeasurementsFlat(case["spike_times"], case["spike_counts"])
-    model.setELLCalculationParams({"leg_quad_points": torch.as_tensor(np.asarray(case["leg_quad_points"])),
-                                   "leg_quad_weights": torch.as_tensor(np.asarray(case["leg_quad_weights"]))})
+    tt = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+    model.setELLCalculationParams({"leg_quad_points": tt(case["leg_quad_points"]),
+                                   "leg_quad_weights": tt(case["leg_quad_weights"])})
     model.setPriorCovRegParam(case["reg"])
     model.buildKernelsMatrices()
     return model

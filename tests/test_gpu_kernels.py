@@ -1,0 +1,109 @@
+"""Stage-level checks of individual C-ABI entry points on the GPU against the numpy restatement
+(oracle/analytic_np.py) and libdevice."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from svgpfa_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_exp_neg_accuracy():
+    """The library's exp for non-positive arguments vs libdevice exp: <= 4e-16 relative over the whole
+    range a covariance kernel can produce; flush-to-zero only below 2^-1021."""
+    from svgpfa_b200 import _cabi
+    lib = _cabi.lib()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.cat([-torch.rand(200000, generator=gen, dtype=torch.float64) * 40.0,
+                   -torch.rand(100000, generator=gen, dtype=torch.float64) * 700.0,
+                   -torch.rand(100000, generator=gen, dtype=torch.float64) * 1e-3,
+                   torch.tensor([0.0, -1e-300, -708.0, -709.5, -745.0, -800.0, -1e6, -1e300],
+                                dtype=torch.float64)]).to(dev)
+    yf, yr = torch.empty_like(x), torch.empty_like(x)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _cabi.check(lib.svgpfa_exp_neg_eval(x.data_ptr(), yf.data_ptr(), yr.data_ptr(), x.numel(), stream))
+    torch.cuda.synchronize()
+    x, yf, yr = x.cpu().numpy(), yf.cpu().numpy(), yr.cpu().numpy()
+    truth = np.exp(x)
+    normal = truth > 2.0 ** -1020
+    err = np.abs(yf[normal] - truth[normal]) / truth[normal]
+    assert err.max() <= 4e-16, err.max()
+    assert np.all(yf[~normal] <= 2.0 ** -1019) and np.all(yf[~normal] >= 0.0)
+    assert yf[x == 0.0][0] == 1.0
+    # libdevice itself, for scale
+    err_ref = np.abs(yr[normal] - truth[normal]) / truth[normal]
+    assert err_ref.max() <= 4e-16
+
+
+@pytest.mark.parametrize("name", ["tiny_mixed", "matlab_r5"])
+def test_stage_buffers_match_numpy_restatement(name):
+    """Li, X, c, alpha, KL_rk, mu/var at quadrature points, abar (spike) against oracle/analytic_np.py."""
+    from oracle import analytic_np
+    from svgpfa_b200.testing import model_from_case, set_requires_grad
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, name + ".npz"))
+    out = analytic_np.elbo_and_grads(case)
+    fw = out["stages"]["fw"]
+    model = model_from_case(case)
+    set_requires_grad(model)
+    v = model.eval()
+    torch.cuda.synchronize()
+    ws = {k: t.cpu().numpy() for k, t in model._ws.items()}
+    R, K = model._R, model._K
+    for r in range(R):
+        for k in range(K):
+            M = model._M[k]
+            mo = r * model._MM + model._mmoff[k]
+            vo = r * model._KM + model._moff[k]
+            f = fw[r, k]
+            assert rel_err(ws["L"][mo:mo + M * M].reshape(M, M), f["L"]) <= 1e-12
+            assert rel_err(ws["Li"][mo:mo + M * M].reshape(M, M), f["Li"]) <= 1e-9
+            assert rel_err(ws["X"][mo:mo + M * M].reshape(M, M), f["X"]) <= 1e-9
+            assert rel_err(ws["c"][vo:vo + M], f["c"]) <= 1e-9
+            assert rel_err(ws["alpha"][vo:vo + M], f["alpha"]) <= 1e-8
+            assert abs(ws["kl_rk"][r * K + k] - f["kl"]) <= 1e-9 * abs(f["kl"])
+            abar_s = out["stages"]["bw"][r, k][1]
+            assert rel_err(ws["abar_spk"][vo:vo + M], abar_s) <= 1e-10 or np.linalg.norm(abar_s) == 0
+    Q = model._Q
+    assert rel_err(ws["mu_q"].reshape(R, Q, K), out["quad_latent_mean"]) <= 1e-10
+    assert rel_err(ws["var_q"].reshape(R, Q, K), out["quad_latent_var"]) <= 1e-9
+    assert abs(v.item() - out["elbo"]) <= 1e-10 * abs(out["elbo"])
+
+
+def test_predict_latents_matches_quadrature_stats():
+    """predictLatents at the quadrature nodes reproduces the cached quadrature statistics
+    (svPosteriorOnLatents.py:57-77 vs :79-86)."""
+    from svgpfa_b200.testing import model_from_case
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed.npz"))
+    model = model_from_case(case)
+    mu, var = model.predictLatents(torch.as_tensor(case["leg_quad_points"]))
+    assert rel_err(mu.cpu().numpy(), ref["quad_latent_mean"]) <= 1e-10
+    assert rel_err(var.cpu().numpy(), ref["quad_latent_var"]) <= 1e-9
+    e_mu, e_var = model.predictEmbedding(torch.as_tensor(case["leg_quad_points"]))
+    assert rel_err(e_mu.cpu().numpy(), ref["quad_embedding_mean"]) <= 1e-10
+    assert rel_err(e_var.cpu().numpy(), ref["quad_embedding_var"]) <= 1e-9
+
+
+def test_host_buffer_entry_matches_device_entry():
+    from svgpfa_b200.testing import model_from_case, set_requires_grad, grads_as_dict
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "config2_r8.npz"))
+    model = model_from_case(case)
+    io = model.makeHostIO(pin=True)
+    elbo, h2d, d2h = model.evalAndGradHost(io, copy_static=True)
+    assert abs(elbo - float(ref["elbo"])) <= 1e-10 * abs(float(ref["elbo"]))
+    R, K = model._R, model._K
+    for k in range(K):
+        M = model._M[k]
+        gm = io["gm"][R * model._moff[k]:R * (model._moff[k] + M)].numpy().reshape(R, M, 1)
+        assert rel_err(gm, ref[f"grad_m_{k}"]) <= 1e-8
+        gz = io["gZ"][R * model._moff[k]:R * (model._moff[k] + M)].numpy().reshape(R, M, 1)
+        assert rel_err(gz, ref[f"grad_Z_{k}"]) <= 1e-8
+    h = 8
+    N = model._N
+    assert rel_err(io["shared"][h:h + N * K].numpy().reshape(N, K), ref["grad_C"]) <= 1e-8
+    assert h2d > 0 and d2h > 0
