@@ -21,7 +21,7 @@ inline void stage_mark(int idx, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out) {
-    __shared__ double etab[64];
+    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
     svgpfa_load_exp_tab(etab);
     __syncthreads();
     const double seed = 1e-3 * (threadIdx.x + 1) + 1e-7 * blockIdx.x;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out
 }
 
 __global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n) {
-    __shared__ double etab[64];
+    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
     svgpfa_load_exp_tab(etab);
     __syncthreads();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {

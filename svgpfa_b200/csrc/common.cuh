@@ -11,30 +11,32 @@
 #define SVGPFA_PI 3.14159265358979323846
 
 // exp(x) for x <= 0 -- every covariance-kernel value is exp of a non-positive number.
-// 64-entry table 2^(j/64) (`tab`, SHARED memory) + degree-5 polynomial on |r| <= ln2/128:
-// 11 FP64-pipe operations instead of libdevice's ~17 + special-case branches; relative error < 3e-16
-// (tests/test_gpu_kernels.py::test_exp_neg_accuracy).  Results below 2^-1021 are flushed to zero.
+// On this part an FP64 instruction occupies the warp scheduler's issue port for 2 cycles (measured: cycles
+// per iteration = 2*N_fp64 + N_other, profiles/README.md), so the routine minimises FP64 operations:
+//   n = rint(x * 2048/ln2), r = x - n ln2/2048 (|r| <= 1.7e-4), exp(x) = 2^(n>>11) * T[n & 2047] * (1 + r + r^2/2 + r^3/6)
+// with T = 2^(j/2048) in SHARED memory (16 KB per CTA): 7 FP64 instructions (libdevice exp: ~17 + branches).
+// Relative error <= 3e-16 for x > -40; the single-FMA reduction adds <= 8e-17 |x| (absolute error <= 3e-17).
+// Arguments below -707 return ~1e-307 instead of a subnormal (tests/test_gpu_kernels.py::test_exp_neg_accuracy).
+__constant__ double svgpfa_expc[2] = {SVGPFA_EXP_INV_L, SVGPFA_EXP_L};
+
 __device__ __forceinline__ void svgpfa_load_exp_tab(double* tab) {
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = svgpfa_exp2_tab_g[i];
+    for (int i = threadIdx.x; i < SVGPFA_EXP_TAB_SIZE; i += blockDim.x) tab[i] = svgpfa_exp2_tab_g[i];
 }
 
 __device__ __forceinline__ double svgpfa_exp_neg(double x, const double* __restrict__ tab) {
-    x = fmax(x, -745.0);
+    // clamp to > -707 on the integer pipe (x <= 0: a larger magnitude is a larger unsigned high word)
+    const unsigned hi = min((unsigned)__double2hiint(x), 0xC08617FFu);
+    x = __hiloint2double((int)hi, __double2loint(x));
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest-integer trick
-    const double t = fma(x, SVGPFA_EXP_INV_L, MAGIC);
+    const double t = fma(x, svgpfa_expc[0], MAGIC);
     const double nd = t - MAGIC;
     const int n = __double2loint(t);
-    double r = fma(nd, -SVGPFA_EXP_L_HI, x);
-    r = fma(nd, -SVGPFA_EXP_L_LO, r);
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
+    const double r = fma(nd, -svgpfa_expc[1], x);
+    double q = fma(r, 1.0 / 6.0, 0.5);
     q = fma(q, r, 1.0);
-    const double T = tab[n & 63];
-    const double e = fma(T * r, q, T);                        // T * exp(r)
-    const int m = n >> 6;
-    const double scaled = __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));
-    return (m < -1021) ? 0.0 : scaled;
+    const double T = tab[n & (SVGPFA_EXP_TAB_SIZE - 1)];
+    const double e = fma(T * r, q, T);                        // T * exp(r), in [0.99, 2.01)
+    return __hiloint2double(__double2hiint(e) + ((n >> SVGPFA_EXP_TAB_BITS) << 20), __double2loint(e));
 }
 
 // Per-latent kernel constants derived from theta (kernels.py:33-46, 73-85).

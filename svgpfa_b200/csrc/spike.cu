@@ -13,6 +13,8 @@
 //   abar_j    = sum_n C[n,k] pn_j(n)          (no cross-lane traffic)
 //   dC[n,k]  += sum_j alpha_j pn_j(n)         (one segmented warp reduction per NON-EMPTY segment)
 // and the value of the term is alpha . abar (taken in svgpfa_finalize).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -29,10 +31,69 @@ __device__ __forceinline__ double seg_sum(double v, unsigned same_mask) {
     return v;
 }
 
-template <bool KGRAD>
-__global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
-                                                                    int n_chunks, int chunk) {
-    __shared__ double etab[64];
+// One kernel evaluation and its accumulations for one (spike, inducing point).
+//   pn += kappa;  expquad : p1 += kappa d,              p2 += kappa d^2
+//                 periodic: p1 += kappa sin(2 pi d/p),  p2 += kappa sin^2(pi d/p),  p3 += kappa sin(2 pi d/p) d
+template <bool KGRAD, bool PERIODIC>
+__device__ __forceinline__ void spike_eval(double t, double z, double nh, double invp,
+                                           const double* __restrict__ etab, double& pn, double& p1, double& p2,
+                                           double& p3) {
+    const double dl = t - z;
+    if (!PERIODIC) {
+        const double q = dl * dl;
+        const double kv = svgpfa_exp_neg(nh * q, etab);
+        pn += kv;
+        if (KGRAD) {
+            p1 = fma(kv, dl, p1);
+            p2 = fma(kv, q, p2);
+        }
+    } else {
+        double sn, cs;
+        sincospi(dl * invp, &sn, &cs);
+        const double q = sn * sn;
+        const double kv = svgpfa_exp_neg(nh * q, etab);
+        pn += kv;
+        if (KGRAD) {
+            const double w = kv * (2.0 * sn * cs);
+            p1 += w;
+            p2 = fma(kv, q, p2);
+            p3 = fma(w, dl, p3);
+        }
+    }
+}
+
+// All spikes of one (trial, neuron) segment for one lane.  UNROLL spike times are loaded one iteration ahead
+// of their use (software pipelining: the loads are warp-uniform L1 hits, but their latency would otherwise
+// sit in front of every dependent FP64 chain).
+template <bool KGRAD, bool PERIODIC, int UNROLL>
+__device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int cnt, double z, double nh, double invp,
+                                              const double* __restrict__ etab, double& pn, double& p1, double& p2,
+                                              double& p3) {
+    int i = 0;
+    if (cnt >= UNROLL) {
+        double tn[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) tn[u] = sp[u];
+        for (; i + UNROLL <= cnt; i += UNROLL) {
+            double tc[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) tc[u] = tn[u];
+            if (i + 2 * UNROLL <= cnt) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) tn[u] = sp[i + UNROLL + u];
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) spike_eval<KGRAD, PERIODIC>(tc[u], z, nh, invp, etab, pn, p1, p2, p3);
+        }
+    }
+    for (; i < cnt; ++i) spike_eval<KGRAD, PERIODIC>(sp[i], z, nh, invp, etab, pn, p1, p2, p3);
+}
+
+// UNROLL = spikes per software-pipelined iteration, MINB = resident CTAs per SM asked of ptxas.
+template <bool KGRAD, int UNROLL, int MINB>
+__global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf,
+                                                                          uint32_t flags, int n_chunks, int chunk) {
+    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
     svgpfa_load_exp_tab(etab);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -43,15 +104,15 @@ __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims 
     const bool active = li < dm.KM;
     // (latent, inducing point) of this lane
     int k = 0;
+    const int l = active ? li : dm.KM - 1;
+    while (k + 1 < dm.K && bf.desc[k + 1].moff <= l) ++k;
+    const double z = bf.Z[(size_t)dm.R * bf.desc[k].moff + (size_t)r * bf.desc[k].M + (l - bf.desc[k].moff)];
+    double nh, invp, s2;
+    bool periodic;
     {
-        const int l = active ? li : dm.KM - 1;
-        while (k + 1 < dm.K && bf.desc[k + 1].moff <= l) ++k;
+        const KConst kc = make_kconst(bf.desc[k], bf.theta, bf.kscale, k);
+        nh = kc.nh; invp = kc.invp; s2 = kc.s2; periodic = kc.type == SVGPFA_KERNEL_PERIODIC;
     }
-    const svgpfa_latent_desc ds = bf.desc[k];
-    const int j = (active ? li : dm.KM - 1) - ds.moff;
-    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    const double z = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + j];
-    const double a = active ? bf.alpha[(size_t)r * dm.KM + li] : 0.0;
     // segment structure of the warp (lanes of one latent are contiguous)
     unsigned same = 0;
 #pragma unroll
@@ -63,50 +124,24 @@ __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims 
     const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
     const bool head = active && (lane == 0 || kprev != k);
     const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
+    const double a = active ? s2 * bf.alpha[(size_t)r * dm.KM + li] : 0.0;     // scale^2 alpha_j
 
     const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
     const int64_t* __restrict__ seg = bf.seg_off + (size_t)r * dm.N;
     const double* __restrict__ st = bf.spike_t;
-    double* gC = bf.shared + SVGPFA_SHARED_HDR;
+    const double* __restrict__ Ck = bf.C + k;
+    double* gCk = bf.shared + SVGPFA_SHARED_HDR + k;
     double abar = 0.0, dz = 0.0, d0 = 0.0, d1 = 0.0;
-    const bool periodic = kc.type == SVGPFA_KERNEL_PERIODIC;
     int64_t s1 = seg[nb];
     for (int n = nb; n < ne; ++n) {
         const int64_t s0 = s1;
         s1 = seg[n + 1];
-        if (s1 == s0) continue;
-        const double c = bf.C[(size_t)n * dm.K + k];
+        const int cnt = (int)(s1 - s0);
+        if (cnt == 0) continue;
+        const double c = Ck[(size_t)n * dm.K];
         double pn = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        if (!periodic) {
-#pragma unroll 4
-            for (int64_t s = s0; s < s1; ++s) {
-                const double dl = st[s] - z;
-                const double q = dl * dl;
-                const double kv = svgpfa_exp_neg(kc.nh * q, etab);
-                pn += kv;
-                if (KGRAD) {
-                    const double t = kv * dl;
-                    p1 += t;                      // sum kappa delta
-                    p2 = fma(t, dl, p2);          // sum kappa delta^2
-                }
-            }
-        } else {
-#pragma unroll 2
-            for (int64_t s = s0; s < s1; ++s) {
-                const double dl = st[s] - z;
-                double sn, cs;
-                sincospi(dl * kc.invp, &sn, &cs);
-                const double q = sn * sn;
-                const double kv = svgpfa_exp_neg(kc.nh * q, etab);
-                pn += kv;
-                if (KGRAD) {
-                    const double t = kv * (2.0 * sn * cs);
-                    p1 += t;                      // sum kappa sin(2 pi d/p)
-                    p2 = fma(kv, q, p2);          // sum kappa sin^2
-                    p3 = fma(t, dl, p3);          // sum kappa sin(2 pi d/p) delta
-                }
-            }
-        }
+        if (!periodic) spike_segment<KGRAD, false, UNROLL>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
+        else spike_segment<KGRAD, true, UNROLL>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
         abar = fma(c, pn, abar);
         if (KGRAD) {
             dz = fma(c, p1, dz);
@@ -115,19 +150,21 @@ __global__ void __launch_bounds__(32 * SP_WPB) spike_fwd_bwd_kernel(svgpfa_dims 
         }
         if (need_emb) {
             const double v = seg_sum(pn * a, same);
-            if (head) atomicAdd(gC + (size_t)n * dm.K + k, kc.s2 * v);
+            if (head) atomicAdd(gCk + (size_t)n * dm.K, v);
         }
     }
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     if (active) {
         atomicAdd(bf.abar_spk + (size_t)r * dm.KM + li, kc.s2 * abar);
-        if (KGRAD) {
-            // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin2) * dd
-            if (flags & SVGPFA_GRAD_INDLOCS) atomicAdd(bf.dz_acc + (size_t)r * dm.KM + li, -kc.s2 * a * kc.dd * dz);
-        }
+        // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin 2 pi d/p) * dd
+        if (KGRAD && (flags & SVGPFA_GRAD_INDLOCS))
+            atomicAdd(bf.dz_acc + (size_t)r * dm.KM + li, -a * kc.dd * dz);
     }
     if (KGRAD && (flags & SVGPFA_GRAD_KERNEL)) {
-        const double t0 = seg_sum(active ? kc.s2 * a * kc.dl * d0 : 0.0, same);
-        const double t1 = seg_sum(active ? kc.s2 * a * kc.dp * d1 : 0.0, same);
+        // dkappa/dtheta0 = kappa (d^2 | sin^2) dl (p2);  periodic: dkappa/dtheta1 = kappa sin(2 pi d/p) d dp (p3)
+        const double t0 = seg_sum(active ? a * kc.dl * d0 : 0.0, same);
+        const double t1 = seg_sum(active ? a * kc.dp * d1 : 0.0, same);
         if (head) {
             double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
             atomicAdd(dth, t0);
@@ -207,14 +244,10 @@ __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm
 
 }  // namespace
 
-extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
-    if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd", cudaSuccess);
-    if (dims->R == 0 || dims->S == 0 || dims->N == 0) return SVGPFA_OK;
+template <bool KGRAD, int UNROLL, int MINB>
+static void launch_spike(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st, int nsm) {
     const int LG = (dims->KM + 31) / 32;
     const int gy = (LG + SP_WPB - 1) / SP_WPB;
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     // enough warps to fill the machine a few times over: split every trial's neurons into chunks
     const long target_warps = (long)nsm * 64 * 4;
     long n_chunks = (target_warps + (long)dims->R * LG - 1) / ((long)dims->R * LG);
@@ -223,11 +256,46 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
     const dim3 grid((unsigned)(dims->R * n_chunks), gy);
+    spike_fwd_bwd_kernel<KGRAD, UNROLL, MINB><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, (int)n_chunks, chunk);
+}
+
+// SVGPFA_SPIKE_VARIANT (environment, experiments only) selects the kernel shape: UNROLL*10 + MINB.
+static int spike_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SVGPFA_SPIKE_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
+    if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd", cudaSuccess);
+    if (dims->R == 0 || dims->S == 0 || dims->N == 0) return SVGPFA_OK;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t st = (cudaStream_t)stream;
     const bool kgrad = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
-    if (kgrad)
-        spike_fwd_bwd_kernel<true><<<grid, 32 * SP_WPB, 0, (cudaStream_t)stream>>>(*dims, *buf, flags, (int)n_chunks, chunk);
-    else
-        spike_fwd_bwd_kernel<false><<<grid, 32 * SP_WPB, 0, (cudaStream_t)stream>>>(*dims, *buf, flags, (int)n_chunks, chunk);
+    const int var = spike_variant();
+#define SP_CASE(code, U, MB)                                                     \
+    case code:                                                                   \
+        if (kgrad) launch_spike<true, U, MB>(dims, buf, flags, st, nsm);         \
+        else launch_spike<false, U, MB>(dims, buf, flags, st, nsm);              \
+        break;
+    switch (var) {
+        SP_CASE(24, 2, 4)
+        SP_CASE(26, 2, 6)
+        SP_CASE(28, 2, 8)
+        SP_CASE(44, 4, 4)
+        SP_CASE(46, 4, 6)
+        SP_CASE(48, 4, 8)
+        SP_CASE(84, 8, 4)
+        default:
+            if (kgrad) launch_spike<true, 4, 6>(dims, buf, flags, st, nsm);
+            else launch_spike<false, 4, 6>(dims, buf, flags, st, nsm);
+    }
+#undef SP_CASE
     SVGPFA_CHECK_LAUNCH("spike_fwd_bwd");
     return SVGPFA_OK;
 }
