@@ -10,66 +10,76 @@
 namespace {
 
 // ======================================================================================
-// latent posterior at quadrature points: thread <-> quadrature point, one CTA per (trial, latent)
+// latent posterior at quadrature points, one CTA (4 warps) per (trial, latent).
+//   lane  <-> quadrature point of the current tile,
+//   warp  <-> a PAIR of 4-row blocks (c, nb-1-c) of the triangular M x M factors, so that every warp does the
+//             same number of multiply-adds in every triangular matrix-vector phase; when M <= 16 the spare
+//             warps take further 32-point sub-tiles instead.
+// Matrix entries are warp-uniform 16-byte shared-memory broadcasts, the per-point vectors (k, v, u, w) live in
+// shared memory as [row][point] with an odd stride (conflict-free).  Nothing of size Q x M reaches HBM.
 // ======================================================================================
-constexpr int QL_TQ = 128;            // quadrature points per pass (= threads per CTA)
-constexpr int QL_TQS = QL_TQ + 1;     // odd row stride of the per-point vectors
+constexpr int QL_THREADS = 128;
+constexpr int QL_WARPS = QL_THREADS / 32;
 
-struct QLSmem {
-    double *LiT, *Li, *X, *XT;        // MP x MP each (zero padded), row stride MP
-    double *ks, *vs, *us;             // MP x QL_TQS
-    double *al, *zs;                  // MP
-    double *mb, *vb;                  // QL_TQ
+struct QLGeom {
+    int M, MP, nb, npair, npw, nqs, TQ, TQS;
 };
 
-__host__ __device__ inline size_t ql_smem_bytes(int MP, bool bwd) {
-    size_t n = (size_t)(bwd ? 4 : 2) * MP * MP + (size_t)(bwd ? 3 : 2) * MP * QL_TQS + 2 * MP + 2 * QL_TQ;
-    return n * sizeof(double);
+__host__ __device__ inline QLGeom ql_geom(int M) {
+    QLGeom g;
+    g.M = M;
+    g.MP = round_up(M, 4);
+    g.nb = g.MP / 4;
+    g.npair = (g.nb + 1) / 2;
+    g.npw = g.npair < QL_WARPS ? g.npair : QL_WARPS;      // warps cooperating on one 32-point sub-tile
+    g.nqs = QL_WARPS / g.npw;                             // 32-point sub-tiles per pass
+    g.TQ = 32 * g.nqs;
+    g.TQS = g.TQ + 1;
+    return g;
 }
 
-__device__ __forceinline__ QLSmem ql_carve(double* sm, int MP, bool bwd) {
+__host__ __device__ inline size_t ql_smem_doubles(int Mmax, bool bwd) {
+    // worst case over M <= Mmax of (mats + vectors); vectors shrink as MP grows only through TQ, so take both ends
+    size_t best = 0;
+    for (int M = 1; M <= Mmax; ++M) {
+        const QLGeom g = ql_geom(M);
+        const size_t n = (size_t)(bwd ? 4 : 2) * g.MP * g.MP + (size_t)(bwd ? 3 : 2) * g.MP * g.TQS + 2 * g.MP
+                         + 4 * g.TQ + (size_t)QL_WARPS * g.TQ * 2;
+        if (n > best) best = n;
+    }
+    return best;
+}
+
+struct QLSmem {
+    double *LiT, *X, *Li, *XT;        // MP x MP (zero padded)
+    double *ks, *vs, *us;             // MP x TQS   (ks doubles as w in the backward pass)
+    double *al, *zs;                  // MP
+    double *mb, *vb, *tt, *spare;     // TQ
+    double *part;                     // QL_WARPS x TQ x 2 partial sums
+};
+
+__device__ __forceinline__ QLSmem ql_carve(double* sm, const QLGeom& g, bool bwd) {
     QLSmem s;
-    s.LiT = sm;
-    s.X = s.LiT + MP * MP;
-    double* p = s.X + MP * MP;
-    if (bwd) { s.Li = p; s.XT = p + MP * MP; p += 2 * MP * MP; } else { s.Li = nullptr; s.XT = nullptr; }
-    s.ks = p; p += MP * QL_TQS;
-    s.vs = p; p += MP * QL_TQS;
-    if (bwd) { s.us = p; p += MP * QL_TQS; } else s.us = nullptr;
-    s.al = p; p += MP;
-    s.zs = p; p += MP;
-    s.mb = p; p += QL_TQ;
-    s.vb = p;
+    double* p = sm;
+    s.LiT = p; p += g.MP * g.MP;
+    s.X = p; p += g.MP * g.MP;
+    if (bwd) { s.Li = p; p += g.MP * g.MP; s.XT = p; p += g.MP * g.MP; } else { s.Li = s.XT = nullptr; }
+    s.ks = p; p += g.MP * g.TQS;
+    s.vs = p; p += g.MP * g.TQS;
+    if (bwd) { s.us = p; p += g.MP * g.TQS; } else s.us = nullptr;
+    s.al = p; p += g.MP;
+    s.zs = p; p += g.MP;
+    s.mb = p; p += g.TQ;
+    s.vb = p; p += g.TQ;
+    s.tt = p; p += g.TQ;
+    s.spare = p; p += g.TQ;
+    s.part = p;
     return s;
 }
 
-// out_i = sum_j Mt[j][i] in_j, i.e. out = Mat * in with Mat given TRANSPOSED (Mt[j*MP+i] = Mat[i][j]).
-// lower == true : Mat lower-triangular  (j <= i)     -> j in [0, i0+3]
-// lower == false: Mat upper-triangular  (j >= i)     -> j in [i0, M)
-// 4 outputs per pass; Mt rows are read as 2 x 16-byte broadcasts, `in` is a per-thread column.
-template <bool LOWER, class Out>
-__device__ __forceinline__ void tri_matvec4(const double* __restrict__ Mt, const double* __restrict__ in, int MP,
-                                            int M, int tq, Out out) {
-    for (int i0 = 0; i0 < MP; i0 += 4) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const int jb = LOWER ? 0 : i0;
-        const int je = LOWER ? min(i0 + 4, M) : M;
-        for (int j = jb; j < je; ++j) {
-            const double x = in[j * QL_TQS + tq];
-            const double2 m01 = *reinterpret_cast<const double2*>(Mt + j * MP + i0);
-            const double2 m23 = *reinterpret_cast<const double2*>(Mt + j * MP + i0 + 2);
-            a0 = fma(m01.x, x, a0);
-            a1 = fma(m01.y, x, a1);
-            a2 = fma(m23.x, x, a2);
-            a3 = fma(m23.y, x, a3);
-        }
-        out(i0, a0, a1, a2, a3);
-    }
-}
-
-__device__ __forceinline__ void ql_load_mats(const QLSmem& s, const svgpfa_dims& dm, const svgpfa_buffers& bf,
-                                             const svgpfa_latent_desc& ds, int r, int MP, bool bwd) {
-    const int M = ds.M;
+__device__ __forceinline__ void ql_load_mats(const QLSmem& s, const QLGeom& g, const svgpfa_dims& dm,
+                                             const svgpfa_buffers& bf, const svgpfa_latent_desc& ds, int r, bool bwd) {
+    const int M = g.M, MP = g.MP;
     const size_t mo = (size_t)r * dm.MM + ds.mmoff;
     for (int idx = threadIdx.x; idx < MP * MP; idx += blockDim.x) {
         const int i = idx / MP, j = idx - i * MP;
@@ -88,166 +98,235 @@ __device__ __forceinline__ void ql_load_mats(const QLSmem& s, const svgpfa_dims&
     }
 }
 
-__global__ void __launch_bounds__(QL_TQ) quad_latent_fwd_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
-    extern __shared__ __align__(16) double sm[];
-    const int r = blockIdx.x, k = blockIdx.y;
-    const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, MP = round_up(M, 4);
-    const QLSmem s = ql_carve(sm, MP, false);
-    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    ql_load_mats(s, dm, bf, ds, r, MP, false);
-    __syncthreads();
-    const int tq = threadIdx.x;
-    for (int q0 = 0; q0 < dm.Q; q0 += QL_TQ) {
-        const int q = q0 + tq;
-        if (q < dm.Q) {
-            const double t = bf.tq[(size_t)r * dm.Q + q];
-            double mu = 0.0;
-            for (int j = 0; j < M; ++j) {
-                const double kv = kappa_val(kc, t - s.zs[j]);
-                s.ks[j * QL_TQS + tq] = kv;
-                mu = fma(kv, s.al[j], mu);
-            }
-            double vv = 0.0, uu = 0.0;
-            // v = Li k
-            tri_matvec4<true>(s.LiT, s.ks, MP, M, tq, [&](int i0, double a0, double a1, double a2, double a3) {
-                s.vs[(i0 + 0) * QL_TQS + tq] = a0;
-                s.vs[(i0 + 1) * QL_TQS + tq] = a1;
-                s.vs[(i0 + 2) * QL_TQS + tq] = a2;
-                s.vs[(i0 + 3) * QL_TQS + tq] = a3;
-                vv += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-            });
-            // u = X^T v  (X^T upper-triangular; its transpose is X, row-major)
-            tri_matvec4<false>(s.X, s.vs, MP, M, tq, [&](int, double a0, double a1, double a2, double a3) {
-                uu += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-            });
-            const size_t o = ((size_t)r * dm.Q + q) * dm.K + k;
-            bf.mu_q[o] = mu;
-            bf.var_q[o] = kc.s2 - vv + uu;
-        }
+// One 4-row block of out = Mat * in for this lane's point.  Mt is Mat TRANSPOSED (Mt[j*MP + i] = Mat[i][j]);
+// LOWER: Mat lower-triangular (j <= i), else upper-triangular (j >= i).
+template <bool LOWER>
+__device__ __forceinline__ void tri_block4(const double* __restrict__ Mt, const double* __restrict__ in, int MP, int M,
+                                           int TQS, int col, int blk, double& a0, double& a1, double& a2, double& a3) {
+    const int i0 = 4 * blk;
+    a0 = a1 = a2 = a3 = 0.0;
+    const int jb = LOWER ? 0 : i0;
+    const int je = LOWER ? min(i0 + 4, M) : M;
+    const double* mp = Mt + jb * MP + i0;
+    const double* ip = in + jb * TQS + col;
+#pragma unroll 4
+    for (int j = jb; j < je; ++j) {
+        const double x = *ip;
+        const double2 m01 = *reinterpret_cast<const double2*>(mp);
+        const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
+        a0 = fma(m01.x, x, a0);
+        a1 = fma(m01.y, x, a1);
+        a2 = fma(m23.x, x, a2);
+        a3 = fma(m23.y, x, a3);
+        mp += MP;
+        ip += TQS;
     }
 }
 
-__global__ void __launch_bounds__(QL_TQ) quad_latent_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+// Runs f(blk) for every 4-row block owned by this warp: pairs (c, nb-1-c), c = pw, pw + npw, ...
+template <class F>
+__device__ __forceinline__ void for_my_blocks(const QLGeom& g, int pw, F f) {
+    for (int c = pw; c < g.npair; c += g.npw) {
+        f(c);
+        const int c2 = g.nb - 1 - c;
+        if (c2 != c) f(c2);
+    }
+}
+
+__global__ void __launch_bounds__(QL_THREADS) quad_latent_fwd_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
+    extern __shared__ __align__(16) double sm[];
+    const int r = blockIdx.x, k = blockIdx.y;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const QLGeom g = ql_geom(ds.M);
+    const QLSmem s = ql_carve(sm, g, false);
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+    ql_load_mats(s, g, dm, bf, ds, r, false);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pw = warp % g.npw, qs = warp / g.npw;          // block-pair slot and 32-point sub-tile of this warp
+    const bool warp_on = qs < g.nqs;
+    const int col = qs * 32 + lane;
+    const int M = g.M, MP = g.MP, TQS = g.TQS;
+    __syncthreads();
+    for (int q0 = 0; q0 < dm.Q; q0 += g.TQ) {
+        // phase 0: kernel values, thread (pw, col) takes inducing points pw, pw + npw, ...
+        double mu = 0.0;
+        if (warp_on) {
+            const int q = q0 + col;
+            const double t = (q < dm.Q) ? bf.tq[(size_t)r * dm.Q + q] : 0.0;
+            for (int j = pw; j < MP; j += g.npw) {
+                const double kv = (q < dm.Q && j < M) ? kappa_val(kc, t - s.zs[j]) : 0.0;
+                s.ks[j * TQS + col] = kv;
+                mu = fma(kv, s.al[j], mu);
+            }
+        }
+        __syncthreads();
+        double vv = 0.0, uu = 0.0;
+        if (warp_on) {
+            for_my_blocks(g, pw, [&](int blk) {
+                double a0, a1, a2, a3;
+                tri_block4<true>(s.LiT, s.ks, MP, M, TQS, col, blk, a0, a1, a2, a3);       // v = Li k
+                double* o = s.vs + 4 * blk * TQS + col;
+                o[0] = a0; o[TQS] = a1; o[2 * TQS] = a2; o[3 * TQS] = a3;
+                vv += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            });
+        }
+        __syncthreads();
+        if (warp_on) {
+            for_my_blocks(g, pw, [&](int blk) {
+                double a0, a1, a2, a3;
+                tri_block4<false>(s.X, s.vs, MP, M, TQS, col, blk, a0, a1, a2, a3);        // u = X^T v
+                uu += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            });
+            s.part[(pw * g.TQ + col) * 2 + 0] = mu;
+            s.part[(pw * g.TQ + col) * 2 + 1] = uu - vv;
+        }
+        __syncthreads();
+        if (warp_on && pw == 0) {
+            const int q = q0 + col;
+            if (q < dm.Q) {
+                double m_ = 0.0, d_ = 0.0;
+                for (int w = 0; w < g.npw; ++w) {
+                    m_ += s.part[(w * g.TQ + col) * 2 + 0];
+                    d_ += s.part[(w * g.TQ + col) * 2 + 1];
+                }
+                const size_t o = ((size_t)r * dm.Q + q) * dm.K + k;
+                bf.mu_q[o] = m_;
+                bf.var_q[o] = kc.s2 + d_;
+            }
+        }
+        // the next pass's phase-0 writes (ks, part after 3 more barriers) cannot race with the reads above:
+        // ks is only read in the v phase (two barriers back); part is rewritten after two further barriers.
+    }
+}
+
+// BIG (M > 44): more 4x4 tiles of A than threads, every thread may own a second tile.
+template <bool BIG>
+__global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, MP = round_up(M, 4);
+    const QLGeom g = ql_geom(ds.M);
     const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
-    const QLSmem s = ql_carve(sm, MP, true);
+    const QLSmem s = ql_carve(sm, g, true);
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    ql_load_mats(s, dm, bf, ds, r, MP, true);
-    const int tq = threadIdx.x;
-    // phase-2 ownership: 4x4 tiles of the lower triangle of A, G groups splitting the q range
-    const int nt = MP / 4, ntile = nt * (nt + 1) / 2;
-    const int G = max(1, (int)blockDim.x / ntile);
-    const int my_tile = tq % ntile, my_g = tq / ntile;
-    const bool has_tile = (tq < ntile * G);
-    int ti = 0, tj = 0;
-    {   // decode my_tile -> (ti >= tj)
-        int t = my_tile, row = 0;
+    ql_load_mats(s, g, dm, bf, ds, r, true);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pw = warp % g.npw, qs = warp / g.npw;
+    const bool warp_on = qs < g.nqs;
+    const int col = qs * 32 + lane;
+    const int M = g.M, MP = g.MP, TQS = g.TQS;
+    // ownership of the reduction A = sum_q varbar_q v v^T: 4x4 tiles of the lower triangle, G groups split q
+    const int nt = g.nb, ntile = nt * (nt + 1) / 2;
+    const int G = max(1, QL_THREADS / ntile);
+    const int my_tile = tid % ntile, my_g = tid / ntile;
+    const bool has_tile = tid < ntile * G;
+    const int my_tile2 = tid + QL_THREADS;
+    const bool has_tile2 = BIG && (G == 1) && (my_tile2 < ntile);
+    auto decode = [](int t, int& ti, int& tj) {
+        int row = 0;
         while (t >= row + 1) { t -= row + 1; ++row; }
         ti = row; tj = t;
-    }
-    // M > 44: more tiles than threads (G == 1); threads tq < ntile - blockDim own a second tile
-    const int my_tile2 = tq + (int)blockDim.x;
-    const bool has_tile2 = (G == 1) && (my_tile2 < ntile);
-    int ti2 = 0, tj2 = 0;
-    if (has_tile2) {
-        int t = my_tile2, row = 0;
-        while (t >= row + 1) { t -= row + 1; ++row; }
-        ti2 = row; tj2 = t;
-    }
-    double acc[16], acc2[16];
+    };
+    int ti = 0, tj = 0, ti2 = 0, tj2 = 0;
+    decode(my_tile, ti, tj);
+    if (has_tile2) decode(my_tile2, ti2, tj2);
+    double acc[16], acc2[BIG ? 16 : 1];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { acc[e] = 0.0; acc2[e] = 0.0; }
-    double ab_acc = 0.0, dz_accum = 0.0, th0 = 0.0, th1 = 0.0;
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < (BIG ? 16 : 1); ++e) acc2[e] = 0.0;
+    // per-lane running sums of abar_j / dz_j: lane e of warp (pw, qs) owns the e-th inducing point handled by that warp
+    double ab_own = 0.0, dz_own = 0.0, th0 = 0.0, th1 = 0.0;
     const size_t part_stride = (size_t)dm.R * dm.Q * dm.K;
     __syncthreads();
-    for (int q0 = 0; q0 < dm.Q; q0 += QL_TQ) {
-        const int q = q0 + tq;
-        const bool valid = q < dm.Q;
+    for (int q0 = 0; q0 < dm.Q; q0 += g.TQ) {
+        // phase 0: adjoints of the statistics, kernel values, abar_j = sum_q mubar_q kappa(t_q, z_j)
         double t = 0.0, mbar = 0.0, vbar = 0.0;
-        if (valid) {
-            t = bf.tq[(size_t)r * dm.Q + q];
-            const size_t o = ((size_t)r * dm.Q + q) * dm.K + k;
-            for (int p = 0; p < dm.n_ntiles; ++p) {
-                mbar += bf.mubar_part[p * part_stride + o];
-                vbar += bf.varbar_part[p * part_stride + o];
+        bool valid = false;
+        if (warp_on) {
+            const int q = q0 + col;
+            valid = q < dm.Q;
+            if (valid) {
+                t = bf.tq[(size_t)r * dm.Q + q];
+                const size_t o = ((size_t)r * dm.Q + q) * dm.K + k;
+                for (int p = 0; p < dm.n_ntiles; ++p) {
+                    mbar += bf.mubar_part[p * part_stride + o];
+                    vbar += bf.varbar_part[p * part_stride + o];
+                }
+            }
+            if (pw == 0) { s.vb[col] = vbar; }
+            int e = 0;
+            for (int j = pw; j < MP; j += g.npw, ++e) {
+                const double kv = (valid && j < M) ? kappa_val(kc, t - s.zs[j]) : 0.0;
+                s.ks[j * TQS + col] = kv;
+                const double sa = warp_sum(mbar * kv);
+                if (lane == e) ab_own += sa;
             }
         }
-        s.mb[tq] = mbar;
-        s.vb[tq] = vbar;
-        for (int j = 0; j < MP; ++j) {
-            const double kv = (valid && j < M) ? kappa_val(kc, t - s.zs[j]) : 0.0;
-            s.ks[j * QL_TQS + tq] = kv;
-        }
-        tri_matvec4<true>(s.LiT, s.ks, MP, M, tq, [&](int i0, double a0, double a1, double a2, double a3) {
-            s.vs[(i0 + 0) * QL_TQS + tq] = a0;
-            s.vs[(i0 + 1) * QL_TQS + tq] = a1;
-            s.vs[(i0 + 2) * QL_TQS + tq] = a2;
-            s.vs[(i0 + 3) * QL_TQS + tq] = a3;
-        });
-        if (need_kz) {
-            // u = X^T v ; w = X u - v ; kbar = 2 vbar Li^T w + mubar alpha ; g_j = kbar_j dkappa/ddelta
-            tri_matvec4<false>(s.X, s.vs, MP, M, tq, [&](int i0, double a0, double a1, double a2, double a3) {
-                s.us[(i0 + 0) * QL_TQS + tq] = a0;
-                s.us[(i0 + 1) * QL_TQS + tq] = a1;
-                s.us[(i0 + 2) * QL_TQS + tq] = a2;
-                s.us[(i0 + 3) * QL_TQS + tq] = a3;
-            });
-            // w overwrites us only after the whole matvec (reads us) is done: stage in registers per 4-block
-            // is not possible (w_i needs all u_j, j<=i), so write w into ks' slot? ks is still needed for
-            // abar.  Use a two-step: w -> vs2 := us (safe: block i0 reads u_j for j <= i0+3 only, and
-            // blocks are processed in DESCENDING order so that u_j, j <= i0+3, are still intact).
-            for (int i0 = MP - 4; i0 >= 0; i0 -= 4) {
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                const int je = min(i0 + 4, M);
-                for (int j = 0; j < je; ++j) {
-                    const double x = s.us[j * QL_TQS + tq];
-                    const double2 m01 = *reinterpret_cast<const double2*>(s.XT + j * MP + i0);
-                    const double2 m23 = *reinterpret_cast<const double2*>(s.XT + j * MP + i0 + 2);
-                    a0 = fma(m01.x, x, a0);
-                    a1 = fma(m01.y, x, a1);
-                    a2 = fma(m23.x, x, a2);
-                    a3 = fma(m23.y, x, a3);
-                }
-                s.us[(i0 + 0) * QL_TQS + tq] = a0 - s.vs[(i0 + 0) * QL_TQS + tq];
-                s.us[(i0 + 1) * QL_TQS + tq] = a1 - s.vs[(i0 + 1) * QL_TQS + tq];
-                s.us[(i0 + 2) * QL_TQS + tq] = a2 - s.vs[(i0 + 2) * QL_TQS + tq];
-                s.us[(i0 + 3) * QL_TQS + tq] = a3 - s.vs[(i0 + 3) * QL_TQS + tq];
-            }
-            // kv = Li^T w (Li^T upper; its transpose is Li row-major); ascending blocks read w_i, i >= j0,
-            // and write slot j0..j0+3 AFTER reading -> in place is safe.
-            tri_matvec4<false>(s.Li, s.us, MP, M, tq, [&](int j0, double a0, double a1, double a2, double a3) {
-                const double av[4] = {a0, a1, a2, a3};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = j0 + e;
-                    double g = 0.0;
-                    if (valid && j < M) {
-                        const double kbar = 2.0 * vbar * av[e] + mbar * s.al[j];
-                        double kv, dkd, d0, d1;
-                        kappa_grad(kc, t - s.zs[j], kv, dkd, d0, d1);
-                        g = -kbar * dkd;           // d delta / d z = -1
-                        th0 = fma(kbar, d0, th0);
-                        th1 = fma(kbar, d1, th1);
-                    }
-                    s.us[j * QL_TQS + tq] = g;
-                }
+        __syncthreads();
+        if (warp_on) {
+            for_my_blocks(g, pw, [&](int blk) {
+                double a0, a1, a2, a3;
+                tri_block4<true>(s.LiT, s.ks, MP, M, TQS, col, blk, a0, a1, a2, a3);       // v = Li k
+                double* o = s.vs + 4 * blk * TQS + col;
+                o[0] = a0; o[TQS] = a1; o[2 * TQS] = a2; o[3 * TQS] = a3;
             });
         }
         __syncthreads();
-        // ---- phase 2: reductions over the quadrature points of this pass
+        if (need_kz) {
+            if (warp_on) {
+                for_my_blocks(g, pw, [&](int blk) {
+                    double a0, a1, a2, a3;
+                    tri_block4<false>(s.X, s.vs, MP, M, TQS, col, blk, a0, a1, a2, a3);    // u = X^T v
+                    double* o = s.us + 4 * blk * TQS + col;
+                    o[0] = a0; o[TQS] = a1; o[2 * TQS] = a2; o[3 * TQS] = a3;
+                });
+            }
+            __syncthreads();
+            if (warp_on) {
+                for_my_blocks(g, pw, [&](int blk) {
+                    double a0, a1, a2, a3;
+                    tri_block4<true>(s.XT, s.us, MP, M, TQS, col, blk, a0, a1, a2, a3);    // w = X u - v  (into ks)
+                    double* o = s.ks + 4 * blk * TQS + col;
+                    const double* v = s.vs + 4 * blk * TQS + col;
+                    o[0] = a0 - v[0]; o[TQS] = a1 - v[TQS]; o[2 * TQS] = a2 - v[2 * TQS]; o[3 * TQS] = a3 - v[3 * TQS];
+                });
+            }
+            __syncthreads();
+            if (warp_on) {
+                int e = 0;
+                for_my_blocks(g, pw, [&](int blk) {
+                    double a[4];
+                    tri_block4<false>(s.Li, s.ks, MP, M, TQS, col, blk, a[0], a[1], a[2], a[3]);   // Li^T w
+#pragma unroll
+                    for (int c = 0; c < 4; ++c, ++e) {
+                        const int j = 4 * blk + c;
+                        double gz = 0.0;
+                        if (valid && j < M) {
+                            const double kbar = 2.0 * vbar * a[c] + mbar * s.al[j];
+                            double kv, dkd, d0, d1;
+                            kappa_grad(kc, t - s.zs[j], kv, dkd, d0, d1);
+                            gz = -kbar * dkd;                        // d delta / d z = -1
+                            th0 = fma(kbar, d0, th0);
+                            th1 = fma(kbar, d1, th1);
+                        }
+                        const double sz = warp_sum(gz);
+                        if (lane == e) dz_own += sz;
+                    }
+                });
+            }
+        }
+        // phase 5: A += sum_q varbar_q v_q v_q^T over the points of this pass (vs is complete since the barrier
+        // after the v phase; vb since the first barrier)
         if (has_tile) {
-            for (int qq = my_g; qq < QL_TQ; qq += G) {
+            for (int qq = my_g; qq < g.TQ; qq += G) {
                 const double sv = s.vb[qq];
                 double vi[4], vj[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    vi[e] = s.vs[(4 * ti + e) * QL_TQS + qq] * sv;
-                    vj[e] = s.vs[(4 * tj + e) * QL_TQS + qq];
+                    vi[e] = s.vs[(4 * ti + e) * TQS + qq] * sv;
+                    vj[e] = s.vs[(4 * tj + e) * TQS + qq];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -255,68 +334,81 @@ __global__ void __launch_bounds__(QL_TQ) quad_latent_bwd_kernel(svgpfa_dims dm, 
                     for (int b = 0; b < 4; ++b) acc[a * 4 + b] = fma(vi[a], vj[b], acc[a * 4 + b]);
             }
         }
-        if (has_tile2) {
-            for (int qq = 0; qq < QL_TQ; ++qq) {
+        if (BIG && has_tile2) {
+            for (int qq = 0; qq < g.TQ; ++qq) {
                 const double sv = s.vb[qq];
                 double vi[4], vj[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    vi[e] = s.vs[(4 * ti2 + e) * QL_TQS + qq] * sv;
-                    vj[e] = s.vs[(4 * tj2 + e) * QL_TQS + qq];
+                    vi[e] = s.vs[(4 * ti2 + e) * TQS + qq] * sv;
+                    vj[e] = s.vs[(4 * tj2 + e) * TQS + qq];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc2[a * 4 + b] = fma(vi[a], vj[b], acc2[a * 4 + b]);
+                    for (int b = 0; b < 4; ++b) acc2[BIG ? a * 4 + b : 0] = fma(vi[a], vj[b], acc2[BIG ? a * 4 + b : 0]);
             }
-        }
-        if (tq < M) {
-            double sa = 0.0, sz = 0.0;
-            for (int qq = 0; qq < QL_TQ; ++qq) {
-                sa = fma(s.mb[qq], s.ks[tq * QL_TQS + qq], sa);
-                if (need_kz) sz += s.us[tq * QL_TQS + qq];
-            }
-            ab_acc += sa;
-            dz_accum += sz;
         }
         __syncthreads();
     }
-    // ---- write-out: combine the G partial copies of every A tile through shared memory
-    double* scratch = s.ks;               // >= ntile*16 doubles?  MP*QL_TQS >= (MP/4)(MP/4+1)/2*16 for MP >= 4
+    // ---- write-out.  A: combine the G partial copies of every tile through shared memory (ks is free now)
+    double* scratch = s.ks;
     const size_t mo = (size_t)r * dm.MM + ds.mmoff;
-    for (int g = 0; g < G; ++g) {
-        if (has_tile && my_g == g) {
+    for (int gi = 0; gi < G; ++gi) {
+        if (has_tile && my_g == gi) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                if (g == 0) scratch[my_tile * 16 + e] = acc[e];
+                if (gi == 0) scratch[my_tile * 16 + e] = acc[e];
                 else scratch[my_tile * 16 + e] += acc[e];
             }
         }
         __syncthreads();
     }
-    if (has_tile2) {
+    if (BIG && has_tile2) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) scratch[my_tile2 * 16 + e] = acc2[e];
+        for (int e = 0; e < 16; ++e) scratch[my_tile2 * 16 + e] = acc2[BIG ? e : 0];
     }
     __syncthreads();
-    for (int idx = tq; idx < ntile * 16; idx += blockDim.x) {
+    for (int idx = tid; idx < ntile * 16; idx += QL_THREADS) {
         const int tl = idx / 16, e = idx - tl * 16;
-        int t2 = tl, row = 0;
-        while (t2 >= row + 1) { t2 -= row + 1; ++row; }
-        const int i = 4 * row + e / 4, j = 4 * t2 + (e & 3);
+        int a_, b_;
+        decode(tl, a_, b_);
+        const int i = 4 * a_ + e / 4, j = 4 * b_ + (e & 3);
         if (i < M && j <= i) bf.A_q[mo + (size_t)i * M + j] = scratch[idx];
     }
+    // abar / dz: the q sub-tiles (qs) hold partial sums for the same inducing points -> combine through smem
+    double* comb = s.vs;                 // [2][nqs][MP]
+    __syncthreads();
+    if (warp_on) {
+        // inducing points of this warp, in the order they were enumerated above
+        int e = 0;
+        for (int j = pw; j < MP; j += g.npw, ++e)
+            if (lane == e) comb[(0 * g.nqs + qs) * MP + j] = ab_own;
+        if (need_kz) {
+            e = 0;
+            for_my_blocks(g, pw, [&](int blk) {
+                for (int c = 0; c < 4; ++c, ++e)
+                    if (lane == e) comb[(1 * g.nqs + qs) * MP + 4 * blk + c] = dz_own;
+            });
+        }
+    }
+    __syncthreads();
     const size_t vo = (size_t)r * dm.KM + ds.moff;
-    if (tq < M) {
-        bf.abar_q[vo + tq] = ab_acc;
-        if (need_kz) bf.dz_acc[vo + tq] = dz_accum;      // first writer of dz_acc (spike kernel adds later)
+    if (tid < M) {
+        double sa = 0.0, sz = 0.0;
+        for (int q = 0; q < g.nqs; ++q) {
+            sa += comb[(0 * g.nqs + q) * MP + tid];
+            if (need_kz) sz += comb[(1 * g.nqs + q) * MP + tid];
+        }
+        bf.abar_q[vo + tid] = sa;
+        if (need_kz) bf.dz_acc[vo + tid] = sz;            // first writer of dz_acc (the spike kernel adds later)
     }
     if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
         const double s0 = block_sum(th0, red);
         const double s1 = block_sum(th1, red);
-        if (tq == 0) {
+        if (tid == 0) {
             double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            dth[0] = s0;                                 // first writer of dth_part
+            dth[0] = s0;                                  // first writer of dth_part
             if (ds.nth > 1) dth[1] = s1;
         }
     }
@@ -471,9 +563,9 @@ __global__ void __launch_bounds__(EM_THREADS) quad_embed_kernel(svgpfa_dims dm, 
 extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
-    const size_t smem = ql_smem_bytes(round_up(dims->Mmax, 4), false);
+    const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, false);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    quad_latent_fwd_kernel<<<dim3(dims->R, dims->K), QL_TQ, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    quad_latent_fwd_kernel<<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     SVGPFA_CHECK_LAUNCH("quad_latent_fwd");
     return SVGPFA_OK;
 }
@@ -481,10 +573,15 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
 extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    const size_t smem = ql_smem_bytes(round_up(dims->Mmax, 4), true);
+    const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, true);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_latent_bwd: shared memory", cudaSuccess);
-    cudaFuncSetAttribute(quad_latent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    quad_latent_bwd_kernel<<<dim3(dims->R, dims->K), QL_TQ, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    if (dims->Mmax > 44) {
+        cudaFuncSetAttribute(quad_latent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        quad_latent_bwd_kernel<true><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    } else {
+        cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        quad_latent_bwd_kernel<false><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    }
     SVGPFA_CHECK_LAUNCH("quad_latent_bwd");
     return SVGPFA_OK;
 }

@@ -77,6 +77,23 @@ def test_against_oracle_on_box(name):
     assert worst[0] <= GRAD_TOL, worst
 
 
+@pytest.mark.parametrize("M_list,Q", [([50, 64, 33], 40), ([1, 2, 3], 7), ([17, 16, 13], 33), ([44, 45, 8], 70)])
+def test_inducing_point_counts_up_to_64(M_list, Q):
+    """Every shape class of the per-(trial, latent) kernels: M = 1 .. 64 (north_star: M up to 64), heterogeneous
+    M_k, Q not a multiple of the tile, mixed kernels -- against the oracle executed on the box."""
+    from oracle import svgpfa_oracle as orc
+    cfg = dict(R=3, N=6, K=3, M=max(M_list), Q=Q, mixed=True, ragged=False)
+    case = synthetic.make_case(cfg, seed=21, M_list=M_list, reg=1e-3)
+    # keep Kzz well conditioned for large M: spread the inducing points and shorten the length scale
+    case["kernel_params"][0] = np.array([0.02])
+    case["kernel_params"][2] = np.array([0.03])
+    ref = orc.elbo_and_grads(case)
+    _, out = _eval_all(case)
+    assert abs(out["elbo"] - ref["elbo"]) <= ELBO_TOL * abs(ref["elbo"])
+    worst = max((rel_err(out[key], ref[key]), key) for key in _grad_keys(3))
+    assert worst[0] <= GRAD_TOL, worst
+
+
 @pytest.mark.parametrize("groups", [dict(posterior=True, embedding=False, kernels=False, indlocs=False),
                                     dict(posterior=False, embedding=True, kernels=False, indlocs=False),
                                     dict(posterior=False, embedding=False, kernels=True, indlocs=False),
