@@ -23,7 +23,7 @@ import warnings
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, sharding
 from .kernels import kernel_spec
 
 _F64 = torch.float64
@@ -373,7 +373,7 @@ class B200SVLowerBound:
     def _finish(self, shared):
         if self._pg is not None:
             # the one exchange step of the path: [elbo.. | dC | dd | dtheta] summed over trial shards
-            torch.distributed.all_reduce(shared, group=self._pg)
+            sharding.all_reduce_shared(shared, self._pg)
         if self._check_errors:
             host = torch.cat([shared[:1], self._ws["info"].to(_F64)]).cpu()
             if int(host[1]) == _cabi.INFO_NOT_PD:
@@ -495,7 +495,7 @@ class B200SVLowerBound:
             _cabi.check(_cabi.lib().svgpfa_cached_ell_fwd_bwd(ctypes.byref(self._dims), ctypes.byref(b),
                                                               self._stream()), "cached_ell_fwd_bwd")
         if self._pg is not None:
-            torch.distributed.all_reduce(shared, group=self._pg)
+            sharding.all_reduce_shared(shared, self._pg)
         self._cached_keepalive = (mu_q, var_q, mu_s)
         return shared
 
