@@ -248,3 +248,25 @@ def test_directional_derivative_full_shape():
                 p.add_(u, alpha=-sgn * eps)
     fd = (vals[0] - vals[1]) / (2 * eps)
     assert abs(fd - pred) <= 1e-5 * abs(pred), (fd, pred)
+
+
+def test_ecm_driver_trajectory_matches_oracle_model():
+    """The ECM call sequence of SVEM_PyTorch (restated in tests/ecm_driver.py, svEM.py:76-294) driven with
+    torch.optim.LBFGS on the CUDA model and on an oracle-backed CPU model: the lower bound after every step agrees
+    (the optimiser amplifies rounding differences, hence 1e-7 relative here, not the per-evaluation 1e-10)."""
+    import ecm_driver
+    from svgpfa_b200.testing import model_from_case
+    case, _ = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed.npz"))
+    kw = dict(max_iter=8, lr=1.0, tolerance_grad=1e-7, tolerance_change=1e-9, line_search_fn="strong_wolfe")
+    gpu_model = model_from_case(case)
+    hist_gpu, log_gpu = ecm_driver.maximize(gpu_model, em_max_iter=2, lbfgs_kwargs=kw)
+    cpu_model = ecm_driver.OracleModel(case)
+    hist_cpu, log_cpu = ecm_driver.maximize(cpu_model, em_max_iter=2, lbfgs_kwargs=kw)
+    assert hist_gpu[0] == pytest.approx(hist_cpu[0], rel=1e-12)
+    for a, b in zip(log_gpu, log_cpu):
+        assert a[:2] == b[:2]
+        assert a[2] == pytest.approx(b[2], rel=1e-7), (a, b)
+    assert all(y >= x - 1e-9 * abs(x) for x, y in zip(hist_gpu, hist_gpu[1:]))       # ECM never decreases the bound
+    # the fitted parameters agree too
+    for pg, pc in zip(gpu_model.getSVEmbeddingParams(), cpu_model.getSVEmbeddingParams()):
+        assert rel_err(pg.detach().cpu().numpy(), pc.detach().numpy()) <= 1e-5
