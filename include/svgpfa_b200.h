@@ -115,8 +115,8 @@ typedef struct svgpfa_buffers {
     /* ---- quadrature statistics ---------------------------------------------------------- */
     double* mu_q;                /* R*Q*K */
     double* var_q;               /* R*Q*K */
-    double* mubar_part;          /* n_ntiles*R*Q*K  per-neuron-tile partials of dELBO/dmu_q     */
-    double* varbar_part;         /* n_ntiles*R*Q*K                                              */
+    double* mubar_part;          /* n_ntiles*R*K*Q  [tile][r][k][q] per-neuron-tile partials of dELBO/dmu_q */
+    double* varbar_part;         /* n_ntiles*R*K*Q  same layout                                  */
     double* term1_part;          /* SVGPFA_TERM1_SLOTS partial sums of the intensity integral  */
     /* ---- cached-statistics path (embedding M-step) -------------------------------------- */
     double* mu_s;                /* S*K   latent means at spike times, [s][k]                   */

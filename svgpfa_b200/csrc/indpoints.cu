@@ -329,6 +329,7 @@ extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 6, 6);
     cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     indpoints_bwd_kernel<<<dim3(dims->R, dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;

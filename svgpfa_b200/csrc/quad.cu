@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kerne
             valid = q < dm.Q;
             if (valid) {
                 t = bf.tq[(size_t)r * dm.Q + q];
-                const size_t o = ((size_t)r * dm.Q + q) * dm.K + k;
+                const size_t o = ((size_t)r * dm.K + k) * dm.Q + q;          // [tile][r][k][q]: coalesced over q
                 for (int p = 0; p < dm.n_ntiles; ++p) {
                     mbar += bf.mubar_part[p * part_stride + o];
                     vbar += bf.varbar_part[p * part_stride + o];
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(EM_THREADS) quad_embed_kernel(svgpfa_dims dm, 
         // ---- phase B: mubar[q][k] = sum_n G[q][n] C[n][k], varbar = 0.5 sum_n G C^2 (this tile's partial)
         if (need_lat) {
             for (int o = tid; o < EM_TQ * K; o += EM_THREADS) {
-                const int qq = o / K, kk = o - qq * K;
+                const int kk = o / EM_TQ, qq = o - kk * EM_TQ;
                 double sm_ = 0.0, sv_ = 0.0;
                 const double* g = Gs + qq * EM_TNS;
                 const double* c = CT + kk * EM_TNS;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(EM_THREADS) quad_embed_kernel(svgpfa_dims dm, 
                     sv_ = fma(b, c2.y, sv_);
                 }
                 if (q0 + qq < Q) {
-                    const size_t oo = part_off + ((size_t)r * Q + q0 + qq) * K + kk;
+                    const size_t oo = part_off + ((size_t)r * K + kk) * Q + q0 + qq;     // [tile][r][k][q]
                     bf.mubar_part[oo] = sm_;
                     bf.varbar_part[oo] = 0.5 * sv_;
                 }
@@ -565,6 +565,7 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, false);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     quad_latent_fwd_kernel<<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     SVGPFA_CHECK_LAUNCH("quad_latent_fwd");
     return SVGPFA_OK;
@@ -580,6 +581,7 @@ extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buff
         quad_latent_bwd_kernel<true><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     } else {
         cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         quad_latent_bwd_kernel<false><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     }
     SVGPFA_CHECK_LAUNCH("quad_latent_bwd");
@@ -592,6 +594,7 @@ extern "C" int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_b
     const size_t smem = em_smem_bytes(dims->K);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_embed: K too large for shared memory", cudaSuccess);
     cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int ntiles = (dims->N + EM_TN - 1) / EM_TN;
     const int qtiles = (dims->Q + EM_TQ - 1) / EM_TQ;
     const long nitems = (long)dims->R * qtiles;

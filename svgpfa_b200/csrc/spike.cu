@@ -82,6 +82,9 @@ __device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) tn[u] = sp[i + UNROLL + u];
             }
+            // pull the line 32 spikes ahead into L1 (segments of a trial are contiguous, so this also warms the
+            // next segments); without it every fourth iteration waits on an L2 round trip
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + i + 32));
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) spike_eval<KGRAD, PERIODIC>(tc[u], z, nh, invp, etab, pn, p1, p2, p3);
         }
