@@ -14,7 +14,10 @@ constexpr int IP_THREADS = 128;
 __device__ __forceinline__ int ld_of(int M) { return M | 1; }   // odd leading dimension: conflict-free columns
 
 // ------------------------------------------------------------------------------------------
+// ONEWARP (M <= 32): the CTA is a single warp and every barrier is a __syncwarp.
+template <bool ONEWARP>
 __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
+    auto sync = [] { if (ONEWARP) __syncwarp(); else __syncthreads(); };
     extern __shared__ double sm[];
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
@@ -27,12 +30,12 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     const double* z = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
     for (int i = tid; i < M; i += T) zs[i] = z[i];
-    __syncthreads();
+    sync();
     for (int idx = tid; idx < M * M; idx += T) {
         const int i = idx / M, j = idx - i * M;
         if (j <= i) A[i * ld + j] = kappa_val(kc, zs[i] - zs[j]) + (i == j ? dm.reg : 0.0);
     }
-    __syncthreads();
+    sync();
     // left-looking Cholesky, thread i owns row i
     bool bad = false;
     for (int j = 0; j < M; ++j) {
@@ -47,9 +50,9 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
             A[j * ld + j] = dg;
             dinv[j] = 1.0 / dg;
         }
-        __syncthreads();
+        sync();
         if (tid > j && tid < M) A[tid * ld + j] = s * dinv[j];
-        __syncthreads();
+        sync();
     }
     if (bad) {
         if (atomicCAS(bf.info, 0, SVGPFA_INFO_NOT_PD) == 0) { bf.info[1] = r; bf.info[2] = k; }
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
             B[i * ld + c] = (i < c) ? 0.0 : s * dinv[i];
         }
     }
-    __syncthreads();
+    sync();
     double* Lg = bf.L + (size_t)r * dm.MM + ds.mmoff;
     double* Lig = bf.Li + (size_t)r * dm.MM + ds.mmoff;
     for (int idx = tid; idx < M * M; idx += T) {
@@ -130,12 +133,26 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_fwd_kernel(svgpfa_dims d
 }
 
 // ------------------------------------------------------------------------------------------
-// out(i,j) for all (i,j) with pred(i,j): one output element per thread-iteration.
-template <class F>
-__device__ __forceinline__ void for_each_ij(int M, bool lower_only, F f) {
-    for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
-        const int i = idx / M, j = idx - i * M;
-        if (!lower_only || j <= i) f(i, j);
+// C(i,j) = sum_{p in [lo,hi]} a(i,p) b(p,j) over 2x4 register tiles (6 shared-memory loads per 8 FMAs).  The
+// matrices are stored full with explicit zeros outside their triangle and zero padding up to MP (multiple of
+// 4), so a tile may use the union [lo, hi] of its elements' ranges.  range(i0, j0, lo, hi) gives that union for
+// the tile whose top-left element is (i0, j0); out(i, j, value) consumes every element of the tile.
+template <class FA, class FB, class FR, class FO>
+__device__ __forceinline__ void mm_tiles(int MP, FA a, FB b, FR range, FO out) {
+    const int tj = MP / 4, ntile = (MP / 2) * tj;
+    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
+        const int i0 = 2 * (t / tj), j0 = 4 * (t - (t / tj) * tj);
+        int lo, hi;
+        range(i0, j0, lo, hi);
+        double c00 = 0, c01 = 0, c02 = 0, c03 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0;
+        for (int p = lo; p <= hi; ++p) {
+            const double a0 = a(i0, p), a1 = a(i0 + 1, p);
+            const double b0 = b(p, j0), b1 = b(p, j0 + 1), b2 = b(p, j0 + 2), b3 = b(p, j0 + 3);
+            c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c02 = fma(a0, b2, c02); c03 = fma(a0, b3, c03);
+            c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11); c12 = fma(a1, b2, c12); c13 = fma(a1, b3, c13);
+        }
+        out(i0, j0, c00); out(i0, j0 + 1, c01); out(i0, j0 + 2, c02); out(i0, j0 + 3, c03);
+        out(i0 + 1, j0, c10); out(i0 + 1, j0 + 1, c11); out(i0 + 1, j0 + 2, c12); out(i0 + 1, j0 + 3, c13);
     }
 }
 
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     __shared__ double red[32];
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, ld = ld_of(M), MS = M * ld;
+    const int M = ds.M, MP = round_up(M, 4), ld = MP + 1, MS = MP * ld;
     const bool need_post = flags & SVGPFA_GRAD_POSTERIOR;
     const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
     double* Lm = sm;             // L
@@ -154,137 +171,137 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     double* B4 = B3 + MS;
     double* B5 = B4 + MS;
     double* al = B5 + MS;        // alpha
-    double* cv = al + M;         // c
-    double* yv = cv + M;         // Li abar
-    double* mb = yv + M;         // mbar
-    double* ab = mb + M;         // abar total
-    double* zs = ab + M;         // z
+    double* cv = al + MP;        // c
+    double* yv = cv + MP;        // Li abar
+    double* mb = yv + MP;        // mbar
+    double* ab = mb + MP;        // abar total
+    double* zs = ab + MP;        // z
     const int tid = threadIdx.x, T = blockDim.x;
     const size_t mo = (size_t)r * dm.MM + ds.mmoff, vo = (size_t)r * dm.KM + ds.moff;
-    for (int idx = tid; idx < M * M; idx += T) {
-        const int i = idx / M, j = idx - i * M;
-        Lm[i * ld + j] = bf.L[mo + idx];
-        Li[i * ld + j] = bf.Li[mo + idx];
-        X[i * ld + j] = bf.X[mo + idx];
+    for (int idx = tid; idx < MP * MP; idx += T) {
+        const int i = idx / MP, j = idx - i * MP;
+        const bool in = i < M && j < M;
+        const size_t g = mo + (size_t)i * M + j;
+        Lm[i * ld + j] = in ? bf.L[g] : 0.0;
+        Li[i * ld + j] = in ? bf.Li[g] : 0.0;
+        X[i * ld + j] = in ? bf.X[g] : 0.0;
         // A_q is stored lower; mirror it
-        B3[i * ld + j] = (j <= i) ? bf.A_q[mo + idx] : bf.A_q[mo + (size_t)j * M + i];
+        B3[i * ld + j] = in ? ((j <= i) ? bf.A_q[g] : bf.A_q[mo + (size_t)j * M + i]) : 0.0;
     }
     const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
-    for (int i = tid; i < M; i += T) {
-        al[i] = bf.alpha[vo + i];
-        cv[i] = bf.c[vo + i];
-        ab[i] = bf.abar_q[vo + i] + bf.abar_spk[vo + i];
-        zs[i] = zg[i];
+    for (int i = tid; i < MP; i += T) {
+        const bool in = i < M;
+        al[i] = in ? bf.alpha[vo + i] : 0.0;
+        cv[i] = in ? bf.c[vo + i] : 0.0;
+        ab[i] = in ? bf.abar_q[vo + i] + bf.abar_spk[vo + i] : 0.0;
+        zs[i] = in ? zg[i] : 0.0;
     }
     __syncthreads();
     // y = Li abar ; cbar = y - c
-    for (int i = tid; i < M; i += T) {
+    for (int i = tid; i < MP; i += T) {
         double s = 0.0;
         for (int p = 0; p <= i; ++p) s += Li[i * ld + p] * ab[p];
         yv[i] = s;
     }
-    // Xbar = tril(2 A X) - X   -> B4
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        if (j <= i) {
-            for (int p = j; p < M; ++p) s += B3[i * ld + p] * X[p * ld + j];
-            s = 2.0 * s - X[i * ld + j];
-        }
-        B4[i * ld + j] = s;
-    });
+    // Xbar = tril(2 A X) - X   -> B4      (A X)(i,j) = sum_{p >= j} A(i,p) X(p,j)
+    mm_tiles(MP, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return X[p * ld + j]; },
+             [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
+             [&](int i, int j, double v) { B4[i * ld + j] = (j <= i) ? 2.0 * v - X[i * ld + j] : 0.0; });
     __syncthreads();
     // mbar = Li^T cbar
-    for (int j = tid; j < M; j += T) {
+    for (int j = tid; j < MP; j += T) {
         double s = 0.0;
-        for (int i = j; i < M; ++i) s += Li[i * ld + j] * (yv[i] - cv[i]);
+        for (int i = j; i < MP; ++i) s += Li[i * ld + j] * (yv[i] - cv[i]);
         mb[j] = s;
     }
-    // T = Li^T tril(Xbar) -> B5  (full matrix needed for T X^T)
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = (i > j ? i : j); p < M; ++p) s += Li[p * ld + i] * B4[p * ld + j];
-        B5[i * ld + j] = s;
-    });
+    // T = Li^T tril(Xbar) -> B5 (full)      T(i,j) = sum_{p >= max(i,j)} Li(p,i) Xbar(p,j)
+    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+             [&](int i0, int j0, int& lo, int& hi) { lo = min(i0, j0); hi = MP - 1; },
+             [&](int i, int j, double v) { B5[i * ld + j] = v; });
     __syncthreads();
     if (need_post) {
         double* gm = bf.gm + (size_t)dm.R * ds.moff + (size_t)r * M;
         for (int i = tid; i < M; i += T) gm[i] = mb[i];
         double* gcv = bf.gcholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
         const double* cvec = bf.cholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
-        for_each_ij(M, true, [&](int i, int j) {
-            const int p = i * (i + 1) / 2 + j;
-            gcv[p] = B5[i * ld + j] + (i == j ? 1.0 / cvec[p] : 0.0);
-        });
+        for (int idx = tid; idx < M * M; idx += T) {
+            const int i = idx / M, j = idx - i * M;
+            if (j <= i) {
+                const int p = i * (i + 1) / 2 + j;
+                gcv[p] = B5[i * ld + j] + (i == j ? 1.0 / cvec[p] : 0.0);
+            }
+        }
     }
     if (!need_kz) return;
-    // B4 = X^T A
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = i; p < M; ++p) s += X[p * ld + i] * B3[p * ld + j];
-        B4[i * ld + j] = s;
-    });
+    // B4 = X^T A      (i,j) = sum_{p >= i} X(p,i) A(p,j)
+    mm_tiles(MP, [&](int i, int p) { return X[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
+             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+             [&](int i, int j, double v) { B4[i * ld + j] = v; });
     __syncthreads();
-    // B3 = E2 = X (X^T A) - A   (in place: each thread touches only its own element of B3)
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = 0; p <= i; ++p) s += X[i * ld + p] * B4[p * ld + j];
-        B3[i * ld + j] = s - B3[i * ld + j];
-    });
+    // B3 = E2 = X (X^T A) - A   (each element of B3 is read and written by its own thread only)
+    mm_tiles(MP, [&](int i, int p) { return X[i * ld + p]; }, [&](int p, int j) { return B4[p * ld + j]; },
+             [&](int i0, int, int& lo, int& hi) { lo = 0; hi = i0 + 1; },
+             [&](int i, int j, double v) { B3[i * ld + j] = v - B3[i * ld + j]; });
     __syncthreads();
     // Lbar (lower) -> B4 = -2 Li^T E2 - alpha y^T - diag(1/L_ii) - T X^T - mbar c^T
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        if (j <= i) {
-            double q = 0.0;
-            for (int p = i; p < M; ++p) q += Li[p * ld + i] * B3[p * ld + j];
-            double t = 0.0;
-            for (int p = 0; p <= j; ++p) t += B5[i * ld + p] * X[j * ld + p];
-            s = -2.0 * q - al[i] * yv[j] - t - mb[i] * cv[j];
-            if (i == j) s -= 1.0 / Lm[i * ld + i];
-        }
-        B4[i * ld + j] = s;
-    });
+    //   first -2 Li^T E2 - ... into B4, then subtract T X^T in a second pass (different operands)
+    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
+             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+             [&](int i, int j, double v) {
+                 double s = 0.0;
+                 if (j <= i && i < M) {
+                     s = -2.0 * v - al[i] * yv[j] - mb[i] * cv[j];
+                     if (i == j) s -= 1.0 / Lm[i * ld + i];
+                 }
+                 B4[i * ld + j] = s;
+             });
     __syncthreads();
-    // P = Phi(L^T Lbar) -> B3 lower, then symmetrise: S = P + P^T
-    for_each_ij(M, true, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = i; p < M; ++p) s += Lm[p * ld + i] * B4[p * ld + j];
-        B3[i * ld + j] = s;            // diagonal: P_ii = s/2, S_ii = s
-    });
+    //   (T X^T)(i,j) = sum_{p <= j} T(i,p) X(j,p)
+    mm_tiles(MP, [&](int i, int p) { return B5[i * ld + p]; }, [&](int p, int j) { return X[j * ld + p]; },
+             [&](int, int j0, int& lo, int& hi) { lo = 0; hi = j0 + 3; },
+             [&](int i, int j, double v) { if (j <= i) B4[i * ld + j] -= v; });
     __syncthreads();
-    for_each_ij(M, false, [&](int i, int j) {
+    // P = Phi(L^T Lbar) -> B3 lower       (i,j) = sum_{p >= i} L(p,i) Lbar(p,j)      (diagonal: P_ii = s/2, S_ii = s)
+    mm_tiles(MP, [&](int i, int p) { return Lm[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+             [&](int i, int j, double v) { if (j <= i) B3[i * ld + j] = v; });
+    __syncthreads();
+    for (int idx = tid; idx < MP * MP; idx += T) {          // S = P + P^T
+        const int i = idx / MP, j = idx - i * MP;
         if (j > i) B3[i * ld + j] = B3[j * ld + i];
-    });
+    }
     __syncthreads();
-    // U1 = S Li -> B4
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = j; p < M; ++p) s += B3[i * ld + p] * Li[p * ld + j];
-        B4[i * ld + j] = s;
-    });
+    // U1 = S Li -> B4      (i,j) = sum_{p >= j} S(i,p) Li(p,j)
+    mm_tiles(MP, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return Li[p * ld + j]; },
+             [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
+             [&](int i, int j, double v) { B4[i * ld + j] = v; });
     __syncthreads();
-    // Kbar = 0.5 Li^T U1 -> B5
-    for_each_ij(M, false, [&](int i, int j) {
-        double s = 0.0;
-        for (int p = i; p < M; ++p) s += Li[p * ld + i] * B4[p * ld + j];
-        B5[i * ld + j] = 0.5 * s;
-    });
+    // Kbar = 0.5 Li^T U1 -> B5      (i,j) = sum_{p >= i} Li(p,i) U1(p,j)
+    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+             [&](int i, int j, double v) { B5[i * ld + j] = 0.5 * v; });
     __syncthreads();
     // dZ_i = 2 sum_j Kbar_ij dkappa/ddelta(z_i - z_j);  dtheta = sum_ij Kbar_ij dkappa/dtheta
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     double t0 = 0.0, t1 = 0.0;
     double* gZ = bf.gZ + (size_t)dm.R * ds.moff + (size_t)r * M;
-    for (int i = tid; i < M; i += T) {
+    // 4 threads per row: thread (i, part) sums j = part, part+4, ... ; combined with two shuffles
+    for (int base = 0; base < M; base += T / 4) {
+        const int i = base + tid / 4, part = tid & 3;
         double dz = 0.0;
-        for (int j = 0; j < M; ++j) {
-            double kv, dkd, d0, d1;
-            kappa_grad(kc, zs[i] - zs[j], kv, dkd, d0, d1);
-            const double kb = B5[i * ld + j];
-            dz += kb * dkd;
-            t0 += kb * d0;
-            t1 += kb * d1;
+        if (i < M) {
+            for (int j = part; j < M; j += 4) {
+                double kv, dkd, d0, d1;
+                kappa_grad(kc, zs[i] - zs[j], kv, dkd, d0, d1);
+                const double kb = B5[i * ld + j];
+                dz += kb * dkd;
+                t0 += kb * d0;
+                t1 += kb * d1;
+            }
         }
-        if (flags & SVGPFA_GRAD_INDLOCS) gZ[i] = 2.0 * dz + bf.dz_acc[vo + i];
+        dz += __shfl_xor_sync(0xffffffffu, dz, 1);
+        dz += __shfl_xor_sync(0xffffffffu, dz, 2);
+        if (i < M && part == 0 && (flags & SVGPFA_GRAD_INDLOCS)) gZ[i] = 2.0 * dz + bf.dz_acc[vo + i];
     }
     if (flags & SVGPFA_GRAD_KERNEL) {
         const double s0 = block_sum(t0, red);
@@ -298,8 +315,8 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
 }
 
 size_t ip_smem(int Mmax, int nmat, int nvec) {
-    const int ld = Mmax | 1;
-    return sizeof(double) * ((size_t)nmat * Mmax * ld + (size_t)nvec * Mmax);
+    const int MP = (Mmax + 3) / 4 * 4, ld = MP + 1;      // covers both the odd-ld and the padded layouts
+    return sizeof(double) * ((size_t)nmat * MP * ld + (size_t)nvec * MP);
 }
 
 }  // namespace
@@ -308,8 +325,13 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M || dims->Mmax < 1) return svgpfa_set_error(SVGPFA_E_ARG, "kzz_chol_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 2, 2);
-    cudaFuncSetAttribute(kzz_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kzz_chol_kernel<<<dim3(dims->R, dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    if (dims->Mmax <= 32) {
+        cudaFuncSetAttribute(kzz_chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kzz_chol_kernel<true><<<dim3(dims->R, dims->K), 32, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    } else {
+        cudaFuncSetAttribute(kzz_chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kzz_chol_kernel<false><<<dim3(dims->R, dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    }
     SVGPFA_CHECK_LAUNCH("kzz_chol_fwd");
     return SVGPFA_OK;
 }
