@@ -62,13 +62,14 @@ __device__ __forceinline__ void spike_eval(double t, double z, double nh, double
     }
 }
 
-// All spikes of one (trial, neuron) segment for one lane.  UNROLL spike times are loaded one iteration ahead
-// of their use (software pipelining: the loads are warp-uniform L1 hits, but their latency would otherwise
-// sit in front of every dependent FP64 chain).
-template <bool KGRAD, bool PERIODIC, int UNROLL>
-__device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int cnt, double z, double nh, double invp,
-                                              const double* __restrict__ etab, double& pn, double& p1, double& p2,
-                                              double& p3) {
+// All spikes of one (trial, neuron) segment for the NP (latent, inducing point) pairs of one lane.  UNROLL spike
+// times are loaded one iteration ahead of their use (software pipelining: the loads are warp-uniform L1 hits, but
+// their latency would otherwise sit in front of every dependent FP64 chain).
+template <bool KGRAD, bool PERIODIC, int UNROLL, int NP>
+__device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int cnt, const double (&z)[NP],
+                                              const double (&nh)[NP], const double (&invp)[NP],
+                                              const double* __restrict__ etab, double (&pn)[NP], double (&p1)[NP],
+                                              double (&p2)[NP], double (&p3)[NP]) {
     int i = 0;
     if (cnt >= UNROLL) {
         double tn[UNROLL];
@@ -86,14 +87,53 @@ __device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int
             // next segments); without it every fourth iteration waits on an L2 round trip
             asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + i + 32));
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) spike_eval<KGRAD, PERIODIC>(tc[u], z, nh, invp, etab, pn, p1, p2, p3);
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    spike_eval<KGRAD, PERIODIC>(tc[u], z[p], nh[p], invp[p], etab, pn[p], p1[p], p2[p], p3[p]);
         }
     }
-    for (; i < cnt; ++i) spike_eval<KGRAD, PERIODIC>(sp[i], z, nh, invp, etab, pn, p1, p2, p3);
+    for (; i < cnt; ++i) {
+        const double t = sp[i];
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            spike_eval<KGRAD, PERIODIC>(t, z[p], nh[p], invp[p], etab, pn[p], p1[p], p2[p], p3[p]);
+    }
 }
 
+// Lane-local description of one (latent, inducing point) pair.
+struct PairInfo {
+    int li, k;
+    bool active, head;
+    unsigned same;
+};
+
+__device__ __forceinline__ PairInfo pair_info(const svgpfa_dims& dm, const svgpfa_buffers& bf, int li, int lane) {
+    PairInfo p;
+    p.li = li;
+    p.active = li < dm.KM;
+    const int l = p.active ? li : dm.KM - 1;
+    int k = 0;
+    while (k + 1 < dm.K && bf.desc[k + 1].moff <= l) ++k;
+    p.k = k;
+    // segment structure of the warp (lanes of one latent are contiguous)
+    unsigned same = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const int ok = __shfl_down_sync(0xffffffffu, k, 1 << b);
+        const int oact = __shfl_down_sync(0xffffffffu, (int)p.active, 1 << b);
+        if (lane + (1 << b) < 32 && ok == k && oact && p.active) same |= 1u << b;
+    }
+    p.same = same;
+    const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    p.head = p.active && (lane == 0 || kprev != k);
+    return p;
+}
+
+// NP = (latent, inducing point) pairs per lane: slot p of a warp covers pairs grp*32*NP + p*32 + lane, so the
+// spike load, the loop and the segment bookkeeping are shared by NP kernel evaluations.
 // UNROLL = spikes per software-pipelined iteration, MINB = resident CTAs per SM asked of ptxas.
-template <bool KGRAD, int UNROLL, int MINB>
+template <bool KGRAD, int UNROLL, int MINB, int NP>
 __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf,
                                                                           uint32_t flags, int n_chunks, int chunk) {
     __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
@@ -102,76 +142,94 @@ __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x / n_chunks, nc = blockIdx.x - r * n_chunks;
     const int grp = blockIdx.y * SP_WPB + warp;
-    const int li = grp * 32 + lane;
-    if (grp * 32 >= dm.KM) return;                       // whole warp out of range
-    const bool active = li < dm.KM;
-    // (latent, inducing point) of this lane
-    int k = 0;
-    const int l = active ? li : dm.KM - 1;
-    while (k + 1 < dm.K && bf.desc[k + 1].moff <= l) ++k;
-    const double z = bf.Z[(size_t)dm.R * bf.desc[k].moff + (size_t)r * bf.desc[k].M + (l - bf.desc[k].moff)];
-    double nh, invp, s2;
-    bool periodic;
-    {
-        const KConst kc = make_kconst(bf.desc[k], bf.theta, bf.kscale, k);
-        nh = kc.nh; invp = kc.invp; s2 = kc.s2; periodic = kc.type == SVGPFA_KERNEL_PERIODIC;
-    }
-    // segment structure of the warp (lanes of one latent are contiguous)
-    unsigned same = 0;
+    if (grp * 32 * NP >= dm.KM) return;                  // whole warp out of range
+    PairInfo pi[NP];
+    double z[NP], nh[NP], invp[NP], a[NP];
+    bool any_periodic = false, all_periodic = true;
 #pragma unroll
-    for (int b = 0; b < 5; ++b) {
-        const int ok = __shfl_down_sync(0xffffffffu, k, 1 << b);
-        const int oact = __shfl_down_sync(0xffffffffu, (int)active, 1 << b);
-        if (lane + (1 << b) < 32 && ok == k && oact && active) same |= 1u << b;
+    for (int p = 0; p < NP; ++p) {
+        pi[p] = pair_info(dm, bf, grp * 32 * NP + p * 32 + lane, lane);
+        const svgpfa_latent_desc ds = bf.desc[pi[p].k];
+        const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi[p].k);
+        const int l = pi[p].active ? pi[p].li : dm.KM - 1;
+        z[p] = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + (l - ds.moff)];
+        nh[p] = kc.nh;
+        invp[p] = kc.invp;
+        a[p] = pi[p].active ? kc.s2 * bf.alpha[(size_t)r * dm.KM + pi[p].li] : 0.0;     // scale^2 alpha_j
+        const bool per = kc.type == SVGPFA_KERNEL_PERIODIC;
+        any_periodic |= per;
+        all_periodic &= per;
     }
-    const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
-    const bool head = active && (lane == 0 || kprev != k);
+    // a lane whose NP pairs mix kernel types takes the general (periodic-capable) path for all of them: the
+    // periodic formula with invp = 0 is NOT the exponential-quadratic one, so mixed lanes evaluate pair by pair
+    const bool mixed = any_periodic && !all_periodic;
     const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
-    const double a = active ? s2 * bf.alpha[(size_t)r * dm.KM + li] : 0.0;     // scale^2 alpha_j
-
     const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
     const int64_t* __restrict__ seg = bf.seg_off + (size_t)r * dm.N;
     const double* __restrict__ st = bf.spike_t;
-    const double* __restrict__ Ck = bf.C + k;
-    double* gCk = bf.shared + SVGPFA_SHARED_HDR + k;
-    double abar = 0.0, dz = 0.0, d0 = 0.0, d1 = 0.0;
+    double* gC = bf.shared + SVGPFA_SHARED_HDR;
+    double abar[NP], dz[NP], d0[NP], d1[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) abar[p] = dz[p] = d0[p] = d1[p] = 0.0;
     int64_t s1 = seg[nb];
     for (int n = nb; n < ne; ++n) {
         const int64_t s0 = s1;
         s1 = seg[n + 1];
         const int cnt = (int)(s1 - s0);
         if (cnt == 0) continue;
-        const double c = Ck[(size_t)n * dm.K];
-        double pn = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        if (!periodic) spike_segment<KGRAD, false, UNROLL>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
-        else spike_segment<KGRAD, true, UNROLL>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
-        abar = fma(c, pn, abar);
-        if (KGRAD) {
-            dz = fma(c, p1, dz);
-            d0 = fma(c, p2, d0);
-            d1 = fma(c, p3, d1);
+        double c[NP], pn[NP], p1[NP], p2[NP], p3[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            c[p] = bf.C[(size_t)n * dm.K + pi[p].k];
+            pn[p] = p1[p] = p2[p] = p3[p] = 0.0;
         }
-        if (need_emb) {
-            const double v = seg_sum(pn * a, same);
-            if (head) atomicAdd(gCk + (size_t)n * dm.K, v);
+        if (!any_periodic) {
+            spike_segment<KGRAD, false, UNROLL, NP>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
+        } else if (!mixed) {
+            spike_segment<KGRAD, true, UNROLL, NP>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const double z1[1] = {z[p]}, nh1[1] = {nh[p]}, ip1[1] = {invp[p]};
+                double q0[1] = {0.0}, q1[1] = {0.0}, q2[1] = {0.0}, q3[1] = {0.0};
+                if (invp[p] == 0.0) spike_segment<KGRAD, false, UNROLL, 1>(st + s0, cnt, z1, nh1, ip1, etab, q0, q1, q2, q3);
+                else spike_segment<KGRAD, true, UNROLL, 1>(st + s0, cnt, z1, nh1, ip1, etab, q0, q1, q2, q3);
+                pn[p] = q0[0]; p1[p] = q1[0]; p2[p] = q2[0]; p3[p] = q3[0];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            abar[p] = fma(c[p], pn[p], abar[p]);
+            if (KGRAD) {
+                dz[p] = fma(c[p], p1[p], dz[p]);
+                d0[p] = fma(c[p], p2[p], d0[p]);
+                d1[p] = fma(c[p], p3[p], d1[p]);
+            }
+            if (need_emb) {
+                const double v = seg_sum(pn[p] * a[p], pi[p].same);
+                if (pi[p].head) atomicAdd(gC + (size_t)n * dm.K + pi[p].k, v);
+            }
         }
     }
-    const svgpfa_latent_desc ds = bf.desc[k];
-    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    if (active) {
-        atomicAdd(bf.abar_spk + (size_t)r * dm.KM + li, kc.s2 * abar);
-        // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin 2 pi d/p) * dd
-        if (KGRAD && (flags & SVGPFA_GRAD_INDLOCS))
-            atomicAdd(bf.dz_acc + (size_t)r * dm.KM + li, -a * kc.dd * dz);
-    }
-    if (KGRAD && (flags & SVGPFA_GRAD_KERNEL)) {
-        // dkappa/dtheta0 = kappa (d^2 | sin^2) dl (p2);  periodic: dkappa/dtheta1 = kappa sin(2 pi d/p) d dp (p3)
-        const double t0 = seg_sum(active ? a * kc.dl * d0 : 0.0, same);
-        const double t1 = seg_sum(active ? a * kc.dp * d1 : 0.0, same);
-        if (head) {
-            double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            atomicAdd(dth, t0);
-            if (ds.nth > 1) atomicAdd(dth + 1, t1);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const svgpfa_latent_desc ds = bf.desc[pi[p].k];
+        const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi[p].k);
+        if (pi[p].active) {
+            atomicAdd(bf.abar_spk + (size_t)r * dm.KM + pi[p].li, kc.s2 * abar[p]);
+            // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin 2 pi d/p) * dd
+            if (KGRAD && (flags & SVGPFA_GRAD_INDLOCS))
+                atomicAdd(bf.dz_acc + (size_t)r * dm.KM + pi[p].li, -a[p] * kc.dd * dz[p]);
+        }
+        if (KGRAD && (flags & SVGPFA_GRAD_KERNEL)) {
+            // dkappa/dtheta0 = kappa (d^2 | sin^2) dl (p2);  periodic: dkappa/dtheta1 = kappa sin(2 pi d/p) d dp (p3)
+            const double t0 = seg_sum(pi[p].active ? a[p] * kc.dl * d0[p] : 0.0, pi[p].same);
+            const double t1 = seg_sum(pi[p].active ? a[p] * kc.dp * d1[p] : 0.0, pi[p].same);
+            if (pi[p].head) {
+                double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
+                atomicAdd(dth, t0);
+                if (ds.nth > 1) atomicAdd(dth + 1, t1);
+            }
         }
     }
 }
@@ -247,9 +305,10 @@ __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm
 
 }  // namespace
 
-template <bool KGRAD, int UNROLL, int MINB>
+template <bool KGRAD, int UNROLL, int MINB, int NP>
 static void launch_spike(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st, int nsm) {
-    const int LG = (dims->KM + 31) / 32;
+    const int per_warp = 32 * NP;
+    const int LG = (dims->KM + per_warp - 1) / per_warp;
     const int gy = (LG + SP_WPB - 1) / SP_WPB;
     // enough warps to fill the machine a few times over: split every trial's neurons into chunks
     const long target_warps = (long)nsm * 64 * 4;
@@ -259,10 +318,10 @@ static void launch_spike(const svgpfa_dims* dims, const svgpfa_buffers* buf, uin
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
     const dim3 grid((unsigned)(dims->R * n_chunks), gy);
-    spike_fwd_bwd_kernel<KGRAD, UNROLL, MINB><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, (int)n_chunks, chunk);
+    spike_fwd_bwd_kernel<KGRAD, UNROLL, MINB, NP><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, (int)n_chunks, chunk);
 }
 
-// SVGPFA_SPIKE_VARIANT (environment, experiments only) selects the kernel shape: UNROLL*10 + MINB.
+// SVGPFA_SPIKE_VARIANT (environment, experiments only) selects the kernel shape: NP*100 + UNROLL*10 + MINB.
 static int spike_variant() {
     static int v = -1;
     if (v < 0) {
@@ -281,22 +340,20 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     cudaStream_t st = (cudaStream_t)stream;
     const bool kgrad = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
     const int var = spike_variant();
-#define SP_CASE(code, U, MB)                                                     \
-    case code:                                                                   \
-        if (kgrad) launch_spike<true, U, MB>(dims, buf, flags, st, nsm);         \
-        else launch_spike<false, U, MB>(dims, buf, flags, st, nsm);              \
+#define SP_CASE(code, U, MB, NP)                                                     \
+    case code:                                                                       \
+        if (kgrad) launch_spike<true, U, MB, NP>(dims, buf, flags, st, nsm);         \
+        else launch_spike<false, U, MB, NP>(dims, buf, flags, st, nsm);              \
         break;
-    switch (var) {
-        SP_CASE(24, 2, 4)
-        SP_CASE(26, 2, 6)
-        SP_CASE(28, 2, 8)
-        SP_CASE(44, 4, 4)
-        SP_CASE(46, 4, 6)
-        SP_CASE(48, 4, 8)
-        SP_CASE(84, 8, 4)
+    switch (var) {          // measured on B200, config #5 shard of 2000 trials: 146 -> 17.1 ms, 126 -> 18.5, 148 -> 17.9,
+                            // 225 -> 17.0, 224 -> 17.8, 243 -> 17.5 (profiles/README.md); the default is 146
+        SP_CASE(126, 2, 6, 1)
+        SP_CASE(148, 4, 8, 1)
+        SP_CASE(225, 2, 5, 2)
+        SP_CASE(243, 4, 3, 2)
         default:
-            if (kgrad) launch_spike<true, 4, 6>(dims, buf, flags, st, nsm);
-            else launch_spike<false, 4, 6>(dims, buf, flags, st, nsm);
+            if (kgrad) launch_spike<true, 4, 6, 1>(dims, buf, flags, st, nsm);
+            else launch_spike<false, 4, 6, 1>(dims, buf, flags, st, nsm);
     }
 #undef SP_CASE
     SVGPFA_CHECK_LAUNCH("spike_fwd_bwd");
