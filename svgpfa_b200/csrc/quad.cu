@@ -428,7 +428,7 @@ __host__ __device__ inline size_t em_smem_bytes(int K) {
     return sizeof(double) * ((size_t)2 * K * EM_TNS + (size_t)EM_TQ * EM_TNS + (size_t)2 * K * EM_TQ + EM_TQ + EM_TN);
 }
 
-__global__ void __launch_bounds__(EM_THREADS) quad_embed_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+__global__ void __launch_bounds__(EM_THREADS, 3) quad_embed_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     const int K = dm.K, N = dm.N, Q = dm.Q;
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(EM_THREADS) quad_embed_kernel(svgpfa_dims dm, 
         }
         __syncthreads();
         // ---- phase B: mubar[q][k] = sum_n G[q][n] C[n][k], varbar = 0.5 sum_n G C^2 (this tile's partial)
+        //      (one output per thread-iteration; a 2-point register tile was measured slower: fewer active threads)
         if (need_lat) {
             for (int o = tid; o < EM_TQ * K; o += EM_THREADS) {
                 const int kk = o / EM_TQ, qq = o - kk * EM_TQ;
@@ -601,7 +602,10 @@ extern "C" int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_b
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    long workers = (long)nsm * 4 / ntiles;
+    int occ = 2;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_kernel, EM_THREADS, smem);
+    if (occ < 1) occ = 1;
+    long workers = (long)nsm * occ / ntiles;           // one resident wave of persistent CTAs
     if (workers < 1) workers = 1;
     if (workers > nitems) workers = nitems;
     quad_embed_kernel<<<dim3(ntiles, (unsigned)workers), EM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
