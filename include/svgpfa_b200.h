@@ -220,7 +220,8 @@ int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, co
  *   Pass NULL to switch recording off.
  * svgpfa_peak_probe: FP64 pipe micro-benchmarks used as roofline denominators (SURVEY.md §8d asks the
  *   builder to MEASURE pi_fma / pi_exp / pi_sin).  kind 0: dependent-chain-free DFMA, 1: libdevice exp,
- *   2: libdevice sincospi, 3: this library's exp (svgpfa_exp_neg).  Launches `blocks` x 256 threads, each
+ *   2: libdevice sincospi, 3: this library's exp (svgpfa_exp_neg), 4: mma.m8n8k4.f64 (8 per thread-iteration,
+ *   32 FMAs per thread each).  Launches `blocks` x 256 threads, each
  *   doing `iters` x 8 operations; the caller times it with events.  out: `blocks*256` doubles (sink). */
 enum { SVGPFA_STAGE_KZZ_CHOL = 0, SVGPFA_STAGE_INDPOINTS_FWD, SVGPFA_STAGE_QUAD_LATENT_FWD, SVGPFA_STAGE_QUAD_EMBED,
        SVGPFA_STAGE_QUAD_LATENT_BWD, SVGPFA_STAGE_SPIKE, SVGPFA_STAGE_INDPOINTS_BWD, SVGPFA_STAGE_FINALIZE,

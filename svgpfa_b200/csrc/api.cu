@@ -44,6 +44,24 @@ __global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 tensor-core probe: 8 independent mma.m8n8k4.f64 accumulator chains per warp (256 FMAs per instruction).
+__global__ void __launch_bounds__(256) dmma_probe_kernel(long iters, double* out) {
+    const double av = 1.0 + 1e-9 * threadIdx.x, bv = 1.0 - 1e-9 * threadIdx.x;
+    double c[8][2];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) c[e][0] = c[e][1] = 1e-3 * e;
+    for (long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[e][0]), "+d"(c[e][1]) : "d"(av), "d"(bv));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += c[e][0] + c[e][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n) {
     __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
     svgpfa_load_exp_tab(etab);
@@ -136,6 +154,7 @@ extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, do
         case 1: peak_probe_kernel<1><<<blocks, 256, 0, st>>>((long)iters, out); break;
         case 2: peak_probe_kernel<2><<<blocks, 256, 0, st>>>((long)iters, out); break;
         case 3: peak_probe_kernel<3><<<blocks, 256, 0, st>>>((long)iters, out); break;
+        case 4: dmma_probe_kernel<<<blocks, 256, 0, st>>>((long)iters, out); break;
         default: return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe kind", cudaSuccess);
     }
     SVGPFA_CHECK_LAUNCH("peak_probe");
