@@ -404,12 +404,15 @@ def run_b200(args):
         sample = synthetic.case_to_numpy(case, 0, r_sub)
         from oracle import svgpfa_oracle as orc
         torch.set_num_threads(threads)
-        t0 = time.perf_counter()
-        ref = orc.elbo_and_grads(sample)
-        dt = time.perf_counter() - t0
+        dt = None
+        for _ in range(2):                                 # first call pays first-touch / thread-pool start-up
+            t0 = time.perf_counter()
+            ref = orc.elbo_and_grads(sample)
+            t_one = time.perf_counter() - t0
+            dt = t_one if dt is None else min(dt, t_one)
         full = dt * R / r_sub
         cpu = {"value": 1.0 / full, "unit": UNIT, "cores": threads, "kind": "port", "cpu": cpu_model_name(),
-               "sample": f"first {r_sub} of {R} trials, one evaluation, time extrapolated linearly to {R} trials",
+               "sample": f"first {r_sub} of {R} trials, best of 2 evaluations, time extrapolated linearly to {R} trials",
                "measured_s_on_sample": dt}
         # parity of the timed configuration on that sample (same inputs, GPU path vs oracle)
         sub = model_from_case(synthetic.case_to_numpy(case, 0, r_sub), device=device)
