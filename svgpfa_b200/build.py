@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libsvgpfa_b200.so")
-SOURCES = ["api.cu", "indpoints.cu", "quad.cu", "spike.cu"]
+SOURCES = ["api.cu", "indpoints.cu", "quad.cu", "quad_mma.cu", "spike.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]

@@ -133,26 +133,30 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_fwd_kernel(svgpfa_dims d
 }
 
 // ------------------------------------------------------------------------------------------
-// C(i,j) = sum_{p in [lo,hi]} a(i,p) b(p,j) over 2x4 register tiles (6 shared-memory loads per 8 FMAs).  The
-// matrices are stored full with explicit zeros outside their triangle and zero padding up to MP (multiple of
-// 4), so a tile may use the union [lo, hi] of its elements' ranges.  range(i0, j0, lo, hi) gives that union for
-// the tile whose top-left element is (i0, j0); out(i, j, value) consumes every element of the tile.
+// C(i,j) = sum_{p in [lo,hi]} a(i,p) b(p,j) on the FP64 tensor path: 8x8 output tiles, one warp per tile,
+// k-steps of 4 (mma.sync.m8n8k4.f64: 256 FMAs for one issue slot and two operand loads).  The matrices are
+// stored full with explicit zeros outside their triangle and zero padding up to MP (multiple of 8), so a tile may
+// use the union [lo, hi] of its elements' ranges.  range(i0, j0, lo, hi) gives that union for the 8x8 tile whose
+// top-left element is (i0, j0); out(i, j, value) consumes every element.  lower_only skips tiles above the diagonal.
+__device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
 template <class FA, class FB, class FR, class FO>
-__device__ __forceinline__ void mm_tiles(int MP, FA a, FB b, FR range, FO out) {
-    const int tj = MP / 4, ntile = (MP / 2) * tj;
-    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
-        const int i0 = 2 * (t / tj), j0 = 4 * (t - (t / tj) * tj);
+__device__ __forceinline__ void mm_mma(int MP, bool lower_only, FA a, FB b, FR range, FO out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int g = lane >> 2, tg = lane & 3, nt = MP / 8;
+    for (int t = warp; t < nt * nt; t += nw) {
+        const int it = t / nt, jt = t - it * nt;
+        if (lower_only && jt > it) continue;
         int lo, hi;
-        range(i0, j0, lo, hi);
-        double c00 = 0, c01 = 0, c02 = 0, c03 = 0, c10 = 0, c11 = 0, c12 = 0, c13 = 0;
-        for (int p = lo; p <= hi; ++p) {
-            const double a0 = a(i0, p), a1 = a(i0 + 1, p);
-            const double b0 = b(p, j0), b1 = b(p, j0 + 1), b2 = b(p, j0 + 2), b3 = b(p, j0 + 3);
-            c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c02 = fma(a0, b2, c02); c03 = fma(a0, b3, c03);
-            c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11); c12 = fma(a1, b2, c12); c13 = fma(a1, b3, c13);
-        }
-        out(i0, j0, c00); out(i0, j0 + 1, c01); out(i0, j0 + 2, c02); out(i0, j0 + 3, c03);
-        out(i0 + 1, j0, c10); out(i0 + 1, j0 + 1, c11); out(i0 + 1, j0 + 2, c12); out(i0 + 1, j0 + 3, c13);
+        range(8 * it, 8 * jt, lo, hi);
+        double c0 = 0.0, c1 = 0.0;
+        for (int ks = lo / 4; ks <= hi / 4; ++ks) dmma8(c0, c1, a(8 * it + g, 4 * ks + tg), b(4 * ks + tg, 8 * jt + g));
+        out(8 * it + g, 8 * jt + 2 * tg, c0);
+        out(8 * it + g, 8 * jt + 2 * tg + 1, c1);
     }
 }
 
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     __shared__ double red[32];
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, MP = round_up(M, 4), ld = MP + 1, MS = MP * ld;
+    const int M = ds.M, MP = round_up(M, 8), ld = MP + 4, MS = MP * ld;       // ld = 4 mod 8: conflict-free fragments
     const bool need_post = flags & SVGPFA_GRAD_POSTERIOR;
     const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
     double* Lm = sm;             // L
@@ -181,12 +185,12 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     for (int idx = tid; idx < MP * MP; idx += T) {
         const int i = idx / MP, j = idx - i * MP;
         const bool in = i < M && j < M;
-        const size_t g = mo + (size_t)i * M + j;
-        Lm[i * ld + j] = in ? bf.L[g] : 0.0;
-        Li[i * ld + j] = in ? bf.Li[g] : 0.0;
-        X[i * ld + j] = in ? bf.X[g] : 0.0;
+        const size_t gi = mo + (size_t)i * M + j;
+        Lm[i * ld + j] = in ? bf.L[gi] : 0.0;
+        Li[i * ld + j] = in ? bf.Li[gi] : 0.0;
+        X[i * ld + j] = in ? bf.X[gi] : 0.0;
         // A_q is stored lower; mirror it
-        B3[i * ld + j] = in ? ((j <= i) ? bf.A_q[g] : bf.A_q[mo + (size_t)j * M + i]) : 0.0;
+        B3[i * ld + j] = in ? ((j <= i) ? bf.A_q[gi] : bf.A_q[mo + (size_t)j * M + i]) : 0.0;
     }
     const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
     for (int i = tid; i < MP; i += T) {
@@ -204,9 +208,9 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
         yv[i] = s;
     }
     // Xbar = tril(2 A X) - X   -> B4      (A X)(i,j) = sum_{p >= j} A(i,p) X(p,j)
-    mm_tiles(MP, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return X[p * ld + j]; },
-             [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
-             [&](int i, int j, double v) { B4[i * ld + j] = (j <= i) ? 2.0 * v - X[i * ld + j] : 0.0; });
+    mm_mma(MP, false, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return X[p * ld + j]; },
+           [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
+           [&](int i, int j, double v) { B4[i * ld + j] = (j <= i) ? 2.0 * v - X[i * ld + j] : 0.0; });
     __syncthreads();
     // mbar = Li^T cbar
     for (int j = tid; j < MP; j += T) {
@@ -215,9 +219,9 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
         mb[j] = s;
     }
     // T = Li^T tril(Xbar) -> B5 (full)      T(i,j) = sum_{p >= max(i,j)} Li(p,i) Xbar(p,j)
-    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-             [&](int i0, int j0, int& lo, int& hi) { lo = min(i0, j0); hi = MP - 1; },
-             [&](int i, int j, double v) { B5[i * ld + j] = v; });
+    mm_mma(MP, false, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+           [&](int i0, int j0, int& lo, int& hi) { lo = max(i0, j0); hi = MP - 1; },
+           [&](int i, int j, double v) { B5[i * ld + j] = v; });
     __syncthreads();
     if (need_post) {
         double* gm = bf.gm + (size_t)dm.R * ds.moff + (size_t)r * M;
@@ -234,37 +238,40 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     }
     if (!need_kz) return;
     // B4 = X^T A      (i,j) = sum_{p >= i} X(p,i) A(p,j)
-    mm_tiles(MP, [&](int i, int p) { return X[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
-             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-             [&](int i, int j, double v) { B4[i * ld + j] = v; });
+    mm_mma(MP, false, [&](int i, int p) { return X[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
+           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+           [&](int i, int j, double v) { B4[i * ld + j] = v; });
     __syncthreads();
     // B3 = E2 = X (X^T A) - A   (each element of B3 is read and written by its own thread only)
-    mm_tiles(MP, [&](int i, int p) { return X[i * ld + p]; }, [&](int p, int j) { return B4[p * ld + j]; },
-             [&](int i0, int, int& lo, int& hi) { lo = 0; hi = i0 + 1; },
-             [&](int i, int j, double v) { B3[i * ld + j] = v - B3[i * ld + j]; });
+    mm_mma(MP, false, [&](int i, int p) { return X[i * ld + p]; }, [&](int p, int j) { return B4[p * ld + j]; },
+           [&](int i0, int, int& lo, int& hi) { lo = 0; hi = i0 + 7; },
+           [&](int i, int j, double v) { B3[i * ld + j] = v - B3[i * ld + j]; });
     __syncthreads();
-    // Lbar (lower) -> B4 = -2 Li^T E2 - alpha y^T - diag(1/L_ii) - T X^T - mbar c^T
-    //   first -2 Li^T E2 - ... into B4, then subtract T X^T in a second pass (different operands)
-    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
-             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-             [&](int i, int j, double v) {
-                 double s = 0.0;
-                 if (j <= i && i < M) {
-                     s = -2.0 * v - al[i] * yv[j] - mb[i] * cv[j];
-                     if (i == j) s -= 1.0 / Lm[i * ld + i];
-                 }
-                 B4[i * ld + j] = s;
-             });
+    // Lbar (lower) -> B4 = -2 Li^T E2 - alpha y^T - diag(1/L_ii) - T X^T - mbar c^T      (two products)
+    mm_mma(MP, true, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
+           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+           [&](int i, int j, double v) {
+               double s = 0.0;
+               if (j <= i && i < M) {
+                   s = -2.0 * v - al[i] * yv[j] - mb[i] * cv[j];
+                   if (i == j) s -= 1.0 / Lm[i * ld + i];
+               }
+               B4[i * ld + j] = s;
+           });
+    for (int idx = tid; idx < MP * MP; idx += T) {            // the skipped upper tiles of Lbar are zero
+        const int i = idx / MP, j = idx - i * MP;
+        if ((j >> 3) > (i >> 3)) B4[i * ld + j] = 0.0;
+    }
     __syncthreads();
     //   (T X^T)(i,j) = sum_{p <= j} T(i,p) X(j,p)
-    mm_tiles(MP, [&](int i, int p) { return B5[i * ld + p]; }, [&](int p, int j) { return X[j * ld + p]; },
-             [&](int, int j0, int& lo, int& hi) { lo = 0; hi = j0 + 3; },
-             [&](int i, int j, double v) { if (j <= i) B4[i * ld + j] -= v; });
+    mm_mma(MP, true, [&](int i, int p) { return B5[i * ld + p]; }, [&](int p, int j) { return X[j * ld + p]; },
+           [&](int, int j0, int& lo, int& hi) { lo = 0; hi = j0 + 7; },
+           [&](int i, int j, double v) { if (j <= i) B4[i * ld + j] -= v; });
     __syncthreads();
     // P = Phi(L^T Lbar) -> B3 lower       (i,j) = sum_{p >= i} L(p,i) Lbar(p,j)      (diagonal: P_ii = s/2, S_ii = s)
-    mm_tiles(MP, [&](int i, int p) { return Lm[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-             [&](int i, int j, double v) { if (j <= i) B3[i * ld + j] = v; });
+    mm_mma(MP, true, [&](int i, int p) { return Lm[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+           [&](int i, int j, double v) { if (j <= i) B3[i * ld + j] = v; });
     __syncthreads();
     for (int idx = tid; idx < MP * MP; idx += T) {          // S = P + P^T
         const int i = idx / MP, j = idx - i * MP;
@@ -272,14 +279,14 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     }
     __syncthreads();
     // U1 = S Li -> B4      (i,j) = sum_{p >= j} S(i,p) Li(p,j)
-    mm_tiles(MP, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return Li[p * ld + j]; },
-             [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
-             [&](int i, int j, double v) { B4[i * ld + j] = v; });
+    mm_mma(MP, false, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return Li[p * ld + j]; },
+           [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
+           [&](int i, int j, double v) { B4[i * ld + j] = v; });
     __syncthreads();
     // Kbar = 0.5 Li^T U1 -> B5      (i,j) = sum_{p >= i} Li(p,i) U1(p,j)
-    mm_tiles(MP, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-             [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-             [&](int i, int j, double v) { B5[i * ld + j] = 0.5 * v; });
+    mm_mma(MP, false, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
+           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
+           [&](int i, int j, double v) { B5[i * ld + j] = 0.5 * v; });
     __syncthreads();
     // dZ_i = 2 sum_j Kbar_ij dkappa/ddelta(z_i - z_j);  dtheta = sum_ij Kbar_ij dkappa/dtheta
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
 }
 
 size_t ip_smem(int Mmax, int nmat, int nvec) {
-    const int MP = (Mmax + 3) / 4 * 4, ld = MP + 1;      // covers both the odd-ld and the padded layouts
+    const int MP = (Mmax + 7) / 8 * 8, ld = MP + 4;      // covers both the odd-ld (M|1) and the padded (MP+4) layouts
     return sizeof(double) * ((size_t)nmat * MP * ld + (size_t)nvec * MP);
 }
 

@@ -5,7 +5,18 @@
 // Ktz (R,Q,M), Kzz^-1 Kzt (R,M,Q) and eLinkValues (R,Q,N) of the reference are never materialised
 // (stats/kernelsMatricesStore.py:186-195, stats/svPosteriorOnLatents.py:185-216,
 //  stats/svEmbedding.py:80-84, stats/expectedLogLikelihood.py:107-135,205-208).
+#include <stdlib.h>
+
 #include "common.cuh"
+
+bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
+                                cudaStream_t st);
+
+static bool use_mma_path() {
+    static int v = -1;
+    if (v < 0) v = getenv("SVGPFA_NO_MMA") ? 0 : 1;       // experiments only: force the CUDA-core kernels
+    return v == 1;
+}
 
 namespace {
 
@@ -564,6 +575,13 @@ __global__ void __launch_bounds__(EM_THREADS, 3) quad_embed_kernel(svgpfa_dims d
 extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
+    // forward: the CUDA-core kernel is still faster (2.48 vs 3.00 ms on the 2000-trial shard); SVGPFA_MMA_FWD=1 forces
+    // the tensor path for experiments
+    static const bool mma_fwd = getenv("SVGPFA_MMA_FWD") != nullptr;
+    if (mma_fwd && use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, 0, false, (cudaStream_t)stream)) {
+        SVGPFA_CHECK_LAUNCH("quad_latent_fwd (mma)");
+        return SVGPFA_OK;
+    }
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, false);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -575,6 +593,10 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
 extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
+    if (use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, flags, true, (cudaStream_t)stream)) {
+        SVGPFA_CHECK_LAUNCH("quad_latent_bwd (mma)");
+        return SVGPFA_OK;
+    }
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, true);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_latent_bwd: shared memory", cudaSuccess);
     if (dims->Mmax > 44) {

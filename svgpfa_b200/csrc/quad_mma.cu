@@ -1,0 +1,401 @@
+// Latent posterior at the quadrature points and its adjoint for M <= 32, on the FP64 tensor path
+// (mma.sync.m8n8k4.f64).  Same arithmetic as quad_latent_{fwd,bwd}_kernel in quad.cu (which stay as the
+// M > 32 path); reference: stats/kernelsMatricesStore.py:186-195, stats/svPosteriorOnLatents.py:185-216.
+//
+// Why the tensor path for a 32 x 32 problem: on this part a DFMA holds the scheduler's issue port for two
+// cycles, so the CUDA-core version of these triangular products is bound by instruction issue and by one
+// shared-memory wavefront per FMA (profiles/README.md).  One m8n8k4 instruction carries 256 FMAs through the
+// same FP64 units (measured: 37.1 TFLOP/s, identical to DFMA) for ONE issue slot and two operand registers.
+//
+// Mapping: CTA <-> (trial, latent); warp <-> a tile of 32 quadrature points, processed without block barriers.
+//   V = Li K,  U = X^T V,  A += V diag(varbar) V^T,  W = X U - V,  Kv = Li^T W       (all 32 x 32 x 32 tiles)
+// The kernel values are generated directly in B-fragment layout (no staging); V, U, W pass through a per-warp
+// shared tile only to change from accumulator layout to B-fragment layout.  Leading dimensions (36) are chosen
+// so that every fragment load/store is bank-conflict free.
+#include "common.cuh"
+
+namespace {
+
+constexpr int QM_WARPS = 4;
+constexpr int QM_LDT = 36;                    // leading dimension of the per-warp 32-point tiles
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
+    const int ld = MP + 4;
+    return (size_t)2 * MP * ld + 2 * MP + (size_t)nw * ((bwd ? 2 : 1) * MP * QM_LDT + 3 * 32);
+}
+
+template <int MT, bool BWD>
+__global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+    constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int r = blockIdx.x, k = blockIdx.y;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const int M = ds.M;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const bool need_kz = BWD && (flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS));
+    double* Lis = sm;                                   // [MP][LD]  Li
+    double* Xs = Lis + MP * LD;                         // [MP][LD]  X
+    double* al = Xs + MP * LD;                          // [MP]
+    double* zs = al + MP;                               // [MP]
+    double* wbase = zs + MP + (size_t)warp * ((BWD ? 2 : 1) * MP * LDT + 3 * 32);
+    double* tileV = wbase;                              // [MP][LDT]
+    double* tileU = wbase + MP * LDT;                   // [MP][LDT]   (BWD only)
+    double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the tile
+    double* mbs = tt + 32;                              // [32] mubar
+    double* vbs = mbs + 32;                             // [32] varbar
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+    {
+        const size_t mo = (size_t)r * dm.MM + ds.mmoff;
+        for (int idx = tid; idx < MP * MP; idx += blockDim.x) {
+            const int i = idx / MP, j = idx - i * MP;
+            const bool in = (i < M) && (j < M);
+            Lis[i * LD + j] = in ? bf.Li[mo + (size_t)i * M + j] : 0.0;
+            Xs[i * LD + j] = in ? bf.X[mo + (size_t)i * M + j] : 0.0;
+        }
+        const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
+        const size_t vo = (size_t)r * dm.KM + ds.moff;
+        for (int i = tid; i < MP; i += blockDim.x) {
+            zs[i] = (i < M) ? zg[i] : 0.0;
+            al[i] = (i < M) ? bf.alpha[vo + i] : 0.0;
+        }
+    }
+    __syncthreads();
+    // persistent accumulators of the adjoint (BWD)
+    constexpr int NTA = MT * (MT + 1) / 2;
+    double accA[BWD ? NTA : 1][2];
+    double abp[BWD ? KS : 1], dzp[BWD ? MT : 1];
+#pragma unroll
+    for (int e = 0; e < (BWD ? NTA : 1); ++e) accA[e][0] = accA[e][1] = 0.0;
+#pragma unroll
+    for (int e = 0; e < (BWD ? KS : 1); ++e) abp[e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < (BWD ? MT : 1); ++e) dzp[e] = 0.0;
+    double th0 = 0.0, th1 = 0.0;
+    const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
+    const int ntq = (dm.Q + 31) / 32;
+    for (int qt0 = warp; qt0 < ntq; qt0 += nw) {
+        const int qbase = qt0 * 32;
+        {   // stage the tile's nodes and statistic adjoints (lane <-> point)
+            const int q = qbase + lane;
+            const bool valid = q < dm.Q;
+            tt[lane] = valid ? bf.tq[(size_t)r * dm.Q + q] : 0.0;
+            if (BWD) {
+                double mbar = 0.0, vbar = 0.0;
+                if (valid) {
+                    const size_t o = ((size_t)r * dm.K + k) * dm.Q + q;
+                    for (int p = 0; p < dm.n_ntiles; ++p) {
+                        mbar += bf.mubar_part[p * part_stride + o];
+                        vbar += bf.varbar_part[p * part_stride + o];
+                    }
+                }
+                mbs[lane] = mbar;
+                vbs[lane] = vbar;
+            }
+        }
+        __syncwarp();
+        // ---- kernel values in B-fragment layout: kf[ks][qt] = kappa(t[8 qt + g] - z[4 ks + tg])
+        double kf[KS][4];
+        {
+            double t4[4];
+            bool v4[4];
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) { t4[qt] = tt[8 * qt + g]; v4[qt] = (qbase + 8 * qt + g) < dm.Q; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int j = 4 * ks + tg;
+                const double zj = zs[j];
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) kf[ks][qt] = (v4[qt] && j < M) ? kappa_val(kc, t4[qt] - zj) : 0.0;
+            }
+        }
+        double mu4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!BWD) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double aj = al[4 * ks + tg];
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) mu4[qt] = fma(kf[ks][qt], aj, mu4[qt]);
+            }
+        } else {
+            double mb4[4];
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) mb4[qt] = mbs[8 * qt + g];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) abp[ks] = fma(mb4[qt], kf[ks][qt], abp[ks]);
+        }
+        // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]
+        double v[MT][4][2];
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt)
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
+                const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, kf[ks][qt]);
+            }
+        }
+        double vv[4][2];
+        if (!BWD) {
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {
+                vv[qt][0] = vv[qt][1] = 0.0;
+#pragma unroll
+                for (int rt = 0; rt < MT; ++rt) {
+                    vv[qt][0] = fma(v[rt][qt][0], v[rt][qt][0], vv[qt][0]);
+                    vv[qt][1] = fma(v[rt][qt][1], v[rt][qt][1], vv[qt][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < MT; ++rt)
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt)
+                *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
+        __syncwarp();
+        // ---- U = X^T V     u[jt][qt] = U[8 jt + g][8 qt + 2 tg + {0,1}]
+        double u[MT][4][2];
+        if (!BWD || need_kz) {
+#pragma unroll
+            for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) u[jt][qt][0] = u[jt][qt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double b[4];
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) b[qt] = tileV[(4 * ks + tg) * LDT + 8 * qt + g];
+#pragma unroll
+                for (int jt = 0; jt <= ks / 2 && jt < MT; ++jt) {    // X^T upper-triangular: k-step ks feeds row tiles <= ks/2
+                    const double a = Xs[(4 * ks + tg) * LD + 8 * jt + g];
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt) dmma(u[jt][qt][0], u[jt][qt][1], a, b[qt]);
+                }
+            }
+        }
+        if (!BWD) {
+            // var = s2 - ||v||^2 + ||u||^2, mu = k . alpha : column sums over the 8 row groups / 4 k groups
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {
+                double d0 = -vv[qt][0], d1 = -vv[qt][1];
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt) {
+                    d0 = fma(u[jt][qt][0], u[jt][qt][0], d0);
+                    d1 = fma(u[jt][qt][1], u[jt][qt][1], d1);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                }
+                double m = mu4[qt];
+                m += __shfl_xor_sync(0xffffffffu, m, 1);
+                m += __shfl_xor_sync(0xffffffffu, m, 2);
+                if (g == 0) {                                      // lanes 0..3 hold columns 8 qt + 2 tg + {0,1}
+                    const int q = qbase + 8 * qt + 2 * tg;
+                    if (q < dm.Q) bf.var_q[((size_t)r * dm.Q + q) * dm.K + k] = kc.s2 + d0;
+                    if (q + 1 < dm.Q) bf.var_q[((size_t)r * dm.Q + q + 1) * dm.K + k] = kc.s2 + d1;
+                }
+                if (tg == 0) {                                     // lanes with tg == 0 hold mu of point 8 qt + g
+                    const int q = qbase + 8 * qt + g;
+                    if (q < dm.Q) bf.mu_q[((size_t)r * dm.Q + q) * dm.K + k] = m;
+                }
+            }
+        } else {
+            // ---- A += V diag(varbar) V^T over the 32 points: k-step = 4 points, A/B fragments from the V tile
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double sv = vbs[4 * ks + tg];
+                double av[MT];
+#pragma unroll
+                for (int it = 0; it < MT; ++it) av[it] = tileV[(8 * it + g) * LDT + 4 * ks + tg];
+#pragma unroll
+                for (int it = 0; it < MT; ++it)
+#pragma unroll
+                    for (int jt = 0; jt <= it; ++jt)
+                        dmma(accA[it * (it + 1) / 2 + jt][0], accA[it * (it + 1) / 2 + jt][1], av[it] * sv, av[jt]);
+            }
+            if (need_kz) {
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt)
+                        *reinterpret_cast<double2*>(tileU + (8 * jt + g) * LDT + 8 * qt + 2 * tg) = make_double2(u[jt][qt][0], u[jt][qt][1]);
+                __syncwarp();
+                // ---- W = X U - V   (accumulators start at -V, re-read in accumulator layout)
+                double w[MT][4][2];
+#pragma unroll
+                for (int it = 0; it < MT; ++it)
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt) {
+                        const double2 vv2 = *reinterpret_cast<const double2*>(tileV + (8 * it + g) * LDT + 8 * qt + 2 * tg);
+                        w[it][qt][0] = -vv2.x;
+                        w[it][qt][1] = -vv2.y;
+                    }
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    double b[4];
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt) b[qt] = tileU[(4 * ks + tg) * LDT + 8 * qt + g];
+#pragma unroll
+                    for (int it = ks / 2; it < MT; ++it) {           // X lower-triangular
+                        const double a = Xs[(8 * it + g) * LD + 4 * ks + tg];
+#pragma unroll
+                        for (int qt = 0; qt < 4; ++qt) dmma(w[it][qt][0], w[it][qt][1], a, b[qt]);
+                    }
+                }
+                __syncwarp();                                        // every lane is done reading U
+#pragma unroll
+                for (int it = 0; it < MT; ++it)
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt)
+                        *reinterpret_cast<double2*>(tileU + (8 * it + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[it][qt][0], w[it][qt][1]);
+                __syncwarp();
+                // ---- Kv = Li^T W, then kbar = 2 varbar Kv + mubar alpha and its products with dkappa
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt) w[jt][qt][0] = w[jt][qt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    double b[4];
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt) b[qt] = tileU[(4 * ks + tg) * LDT + 8 * qt + g];
+#pragma unroll
+                    for (int jt = 0; jt <= ks / 2 && jt < MT; ++jt) {    // Li^T upper-triangular
+                        const double a = Lis[(4 * ks + tg) * LD + 8 * jt + g];
+#pragma unroll
+                        for (int qt = 0; qt < 4; ++qt) dmma(w[jt][qt][0], w[jt][qt][1], a, b[qt]);
+                    }
+                }
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt) {
+                    const int j = 8 * jt + g;
+                    const double zj = zs[j], aj = al[j];
+#pragma unroll
+                    for (int qt = 0; qt < 4; ++qt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int ql = 8 * qt + 2 * tg + e;
+                            const double kbar = 2.0 * vbs[ql] * w[jt][qt][e] + mbs[ql] * aj;
+                            double kval, dkd, d0, d1;
+                            kappa_grad(kc, tt[ql] - zj, kval, dkd, d0, d1);
+                            dzp[jt] = fma(-kbar, dkd, dzp[jt]);      // d delta / d z = -1
+                            th0 = fma(kbar, d0, th0);
+                            th1 = fma(kbar, d1, th1);
+                        }
+                }
+            }
+        }
+        __syncwarp();                                                // tiles are reused by the next pass
+    }
+    if (!BWD) return;
+    // ---- combine the warps through their (now idle) V tiles
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < MT; ++it)
+#pragma unroll
+        for (int jt = 0; jt <= it; ++jt) {
+            const int tl = it * (it + 1) / 2 + jt;
+            tileV[tl * 64 + g * 8 + 2 * tg] = accA[tl][0];
+            tileV[tl * 64 + g * 8 + 2 * tg + 1] = accA[tl][1];
+        }
+    // abar_j = sum over the 8 point groups; dz_j = sum over the 4 column groups
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        double s = abp[ks];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (g == 0) tileV[NTA * 64 + 4 * ks + tg] = s;
+    }
+#pragma unroll
+    for (int jt = 0; jt < MT; ++jt) {
+        double s = dzp[jt];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (tg == 0) tileV[NTA * 64 + MP + 8 * jt + g] = s;
+    }
+    __syncthreads();
+    const size_t wstride = 2 * MP * LDT + 3 * 32;
+    const double* t0p = zs + MP;                                     // warp 0's region
+    const size_t mo = (size_t)r * dm.MM + ds.mmoff;
+    for (int idx = tid; idx < NTA * 64; idx += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += t0p[(size_t)w * wstride + idx];
+        const int tl = idx / 64, e = idx - tl * 64;
+        int it = 0, rem = tl;
+        while (rem >= it + 1) { rem -= it + 1; ++it; }
+        const int i = 8 * it + e / 8, j = 8 * rem + (e & 7);
+        if (i < M && j <= i) bf.A_q[mo + (size_t)i * M + j] = s;
+    }
+    const size_t vo = (size_t)r * dm.KM + ds.moff;
+    if (tid < M) {
+        double sa = 0.0, sz = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            sa += t0p[(size_t)w * wstride + NTA * 64 + tid];
+            sz += t0p[(size_t)w * wstride + NTA * 64 + MP + tid];
+        }
+        bf.abar_q[vo + tid] = sa;
+        if (need_kz) bf.dz_acc[vo + tid] = sz;                       // first writer of dz_acc (the spike kernel adds later)
+    }
+    if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
+        const double s0 = block_sum(th0, red);
+        const double s1 = block_sum(th1, red);
+        if (tid == 0) {
+            double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
+            dth[0] = s0;                                             // first writer of dth_part
+            if (ds.nth > 1) dth[1] = s1;
+        }
+    }
+}
+
+template <int MT, bool BWD>
+void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    int nw = (dims->Q + 31) / 32;
+    if (nw > QM_WARPS) nw = QM_WARPS;
+    if (nw < 1) nw = 1;
+    const size_t smem = sizeof(double) * qm_smem_doubles(8 * MT, nw, BWD);
+    cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    quad_latent_mma_kernel<MT, BWD><<<dim3(dims->R, dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
+}
+
+}  // namespace
+
+// Returns false when the shape is outside this path (M > 32); the caller then uses the CUDA-core kernels.
+bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
+                                cudaStream_t st) {
+    const int M = dims->Mmax;
+    if (M > 32) return false;
+    const int MT = (M + 7) / 8;
+    if (bwd) {
+        switch (MT) {
+            case 1: launch_qm<1, true>(dims, buf, flags, st); break;
+            case 2: launch_qm<2, true>(dims, buf, flags, st); break;
+            case 3: launch_qm<3, true>(dims, buf, flags, st); break;
+            default: launch_qm<4, true>(dims, buf, flags, st); break;
+        }
+    } else {
+        switch (MT) {
+            case 1: launch_qm<1, false>(dims, buf, flags, st); break;
+            case 2: launch_qm<2, false>(dims, buf, flags, st); break;
+            case 3: launch_qm<3, false>(dims, buf, flags, st); break;
+            default: launch_qm<4, false>(dims, buf, flags, st); break;
+        }
+    }
+    return true;
+}
