@@ -12,6 +12,8 @@
 bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
                                 cudaStream_t st);
 
+bool svgpfa_try_quad_embed_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st);
+
 static bool use_mma_path() {
     static int v = -1;
     if (v < 0) v = getenv("SVGPFA_NO_MMA") ? 0 : 1;       // experiments only: force the CUDA-core kernels
@@ -614,6 +616,10 @@ extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buff
 extern "C" int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "quad_embed_fwd_bwd", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0 || dims->N == 0) return SVGPFA_OK;
+    if (use_mma_path() && svgpfa_try_quad_embed_mma(dims, buf, flags, (cudaStream_t)stream)) {
+        SVGPFA_CHECK_LAUNCH("quad_embed_fwd_bwd (mma)");
+        return SVGPFA_OK;
+    }
     const size_t smem = em_smem_bytes(dims->K);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_embed: K too large for shared memory", cudaSuccess);
     cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -374,7 +374,219 @@ void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flag
     quad_latent_mma_kernel<MT, BWD><<<dim3(dims->R, dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
 }
 
+// ======================================================================================
+// embedding + exp link + integral on the tensor path.  Persistent CTA (8 warps) per (128-neuron tile, worker);
+// items = (trial, 16 quadrature points).  Three small GEMMs per item share a shared-memory tile of G = -w exp(.):
+//   A:  H = Mu C^T + d,  Sg = Var (C^2)^T           (16 x 128 x K)    -> G
+//   B:  mubar = G C,  varbar = 1/2 G C^2             (16 x K x 128)    -> per-tile partials in HBM
+//   C:  dC += G^T Mu + C o (G^T Var),  dd += G^T 1    (128 x K x 16)    -> accumulators in registers across items
+// The ones-column trick: column K of the (zero-padded) Mu operand is 1, so dd falls out of GEMM C for free, while
+// row K of C^T is 0 so GEMM A is unaffected.  Same arithmetic as quad_embed_kernel in quad.cu (reference:
+// stats/svEmbedding.py:80-84, stats/expectedLogLikelihood.py:107-135,205-208).
+// ======================================================================================
+constexpr int EMM_TN = SVGPFA_EMBED_TN;       // 128
+constexpr int EMM_TNS = EMM_TN + 4;           // 132 = 4 mod 16: conflict-free fragment loads
+constexpr int EMM_TQ = 16;
+constexpr int EMM_LDQ = 20;                   // leading dimension of the [k][q] statistics tiles
+constexpr int EMM_THREADS = 256;
+
+__host__ __device__ inline int emm_kp(int K) { return (K + 1 + 7) / 8 * 8; }       // K + ones column, padded to 8
+__host__ __device__ inline size_t emm_smem_doubles(int K) {
+    const int KP = emm_kp(K);
+    return (size_t)KP * EMM_TNS + (size_t)EMM_TQ * EMM_TNS + (size_t)2 * KP * EMM_LDQ + EMM_TQ + EMM_TN;
+}
+
+template <int KT>      // KT = KP / 8 k-tiles
+__global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+    constexpr int KP = 8 * KT, KS4 = KP / 4, TNS = EMM_TNS, LDQ = EMM_LDQ;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int K = dm.K, N = dm.N, Q = dm.Q;
+    double* CT = sm;                               // [KP][TNS]   C^T, rows >= K are zero
+    double* Gs = CT + (size_t)KP * TNS;            // [TQ][TNS]
+    double* muT = Gs + (size_t)EMM_TQ * TNS;       // [KP][LDQ]   row K = ones
+    double* varT = muT + (size_t)KP * LDQ;         // [KP][LDQ]
+    double* ws = varT + (size_t)KP * LDQ;          // [TQ]
+    double* dvec = ws + EMM_TQ;                    // [TN]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int tile = blockIdx.x, n0 = tile * EMM_TN;
+    const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
+    const bool need_lat = flags & (SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
+    for (int idx = tid; idx < KP * EMM_TN; idx += EMM_THREADS) {
+        const int kk = idx / EMM_TN, nn = idx - kk * EMM_TN;
+        CT[kk * TNS + nn] = (kk < K && n0 + nn < N) ? bf.C[(size_t)(n0 + nn) * K + kk] : 0.0;
+    }
+    if (tid < EMM_TN) dvec[tid] = (n0 + tid < N) ? bf.d[n0 + tid] : 0.0;
+    // GEMM C accumulators: warp owns neuron tiles {2 warp, 2 warp + 1} x all k-tiles, for Mu and for Var
+    double cm[2][KT][2], cv[2][KT][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < KT; ++b) cm[a][b][0] = cm[a][b][1] = cv[a][b][0] = cv[a][b][1] = 0.0;
+    double t1 = 0.0;
+    const int qtiles = (Q + EMM_TQ - 1) / EMM_TQ;
+    const int nitems = dm.R * qtiles;
+    const size_t part_off = (size_t)tile * dm.R * K * Q;
+    __syncthreads();
+    for (int it = blockIdx.y; it < nitems; it += gridDim.y) {
+        const int r = it / qtiles, q0 = (it - r * qtiles) * EMM_TQ;
+        for (int idx = tid; idx < EMM_TQ * KP; idx += EMM_THREADS) {
+            const int qq = idx / KP, kk = idx - qq * KP;
+            const bool v = (q0 + qq) < Q && kk < K;
+            const size_t o = ((size_t)r * Q + q0 + qq) * K + kk;
+            muT[kk * LDQ + qq] = v ? bf.mu_q[o] : ((kk == K && (q0 + qq) < Q) ? 1.0 : 0.0);
+            varT[kk * LDQ + qq] = v ? bf.var_q[o] : 0.0;
+        }
+        if (tid < EMM_TQ) ws[tid] = (q0 + tid < Q) ? bf.wq[(size_t)r * Q + q0 + tid] : 0.0;
+        __syncthreads();
+        // ---- GEMM A: h[qt][nl] = H[8 qt + g][8 (2 warp + nl) + 2 tg + e]
+        {
+            double h[2][2][2], sg[2][2][2];
+#pragma unroll
+            for (int nl = 0; nl < 2; ++nl) {
+                const double2 d2 = *reinterpret_cast<const double2*>(dvec + 8 * (2 * warp + nl) + 2 * tg);
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) {
+                    h[qt][nl][0] = d2.x; h[qt][nl][1] = d2.y;
+                    sg[qt][nl][0] = sg[qt][nl][1] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS4; ++ks) {
+                double am[2], av[2], bc[2];
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) {
+                    am[qt] = muT[(4 * ks + tg) * LDQ + 8 * qt + g];
+                    av[qt] = varT[(4 * ks + tg) * LDQ + 8 * qt + g];
+                }
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) bc[nl] = CT[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt)
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) {
+                        dmma(h[qt][nl][0], h[qt][nl][1], am[qt], bc[nl]);
+                        dmma(sg[qt][nl][0], sg[qt][nl][1], av[qt], bc[nl] * bc[nl]);
+                    }
+            }
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt) {
+                const double w = ws[8 * qt + g];
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) {
+                    const int nn = 8 * (2 * warp + nl) + 2 * tg;
+                    const double w0 = (n0 + nn < N) ? w : 0.0, w1 = (n0 + nn + 1 < N) ? w : 0.0;
+                    // the ones column contributes muT[K] * CT[K] = 1 * 0 to h: nothing to undo
+                    const double e0 = w0 * exp(fma(0.5, sg[qt][nl][0], h[qt][nl][0]));
+                    const double e1 = w1 * exp(fma(0.5, sg[qt][nl][1], h[qt][nl][1]));
+                    t1 += e0 + e1;
+                    *reinterpret_cast<double2*>(Gs + (8 * qt + g) * TNS + nn) = make_double2(-e0, -e1);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- GEMM B: 2 kinds x 2 point tiles x KT k-tiles, 32 k-steps over the 128 neurons
+        if (need_lat) {
+            for (int u = warp; u < 4 * KT; u += EMM_THREADS / 32) {
+                const int kind = u & 1, qt = (u >> 1) & 1, kt = u >> 2;
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll 8
+                for (int ks = 0; ks < EMM_TN / 4; ++ks) {
+                    const double a = Gs[(8 * qt + g) * TNS + 4 * ks + tg];
+                    const double b = CT[(8 * kt + g) * TNS + 4 * ks + tg];
+                    dmma(c0, c1, a, kind ? b * b : b);
+                }
+                const int q = q0 + 8 * qt + g, kk = 8 * kt + 2 * tg;
+                if (q < Q) {
+                    double* dst = kind ? bf.varbar_part : bf.mubar_part;
+                    const double sc = kind ? 0.5 : 1.0;
+                    if (kk < K) dst[part_off + ((size_t)r * K + kk) * Q + q] = sc * c0;
+                    if (kk + 1 < K) dst[part_off + ((size_t)r * K + kk + 1) * Q + q] = sc * c1;
+                }
+            }
+        }
+        // ---- GEMM C: accumulate G^T Mu and G^T Var over the 16 points (4 k-steps)
+        if (need_emb) {
+#pragma unroll
+            for (int ks = 0; ks < EMM_TQ / 4; ++ks) {
+                double ga[2];
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) ga[nl] = Gs[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    const double bm = muT[(8 * kt + g) * LDQ + 4 * ks + tg];
+                    const double bv = varT[(8 * kt + g) * LDQ + 4 * ks + tg];
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) {
+                        dmma(cm[nl][kt][0], cm[nl][kt][1], ga[nl], bm);
+                        dmma(cv[nl][kt][0], cv[nl][kt][1], ga[nl], bv);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- flush: dC[n][k] = cm + C o cv ; dd[n] = cm[.][K]
+    if (need_emb) {
+        double* gC = bf.shared + SVGPFA_SHARED_HDR;
+        double* gd = gC + (size_t)N * K;
+#pragma unroll
+        for (int nl = 0; nl < 2; ++nl) {
+            const int nn = 8 * (2 * warp + nl) + g, n = n0 + nn;
+            if (n < N) {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kk = 8 * kt + 2 * tg + e;
+                        if (kk < K) atomicAdd(gC + (size_t)n * K + kk, cm[nl][kt][e] + CT[kk * TNS + nn] * cv[nl][kt][e]);
+                        else if (kk == K) atomicAdd(gd + n, cm[nl][kt][e]);
+                    }
+            }
+        }
+    }
+    const double tot = block_sum(t1, red);
+    if (tid == 0) {
+        const int slot = (blockIdx.y * gridDim.x + blockIdx.x) % SVGPFA_TERM1_SLOTS;
+        atomicAdd(bf.term1_part + slot, tot);
+    }
+}
+
+template <int KT>
+void launch_emm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    const size_t smem = sizeof(double) * emm_smem_doubles(dims->K);
+    cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int ntiles = (dims->N + EMM_TN - 1) / EMM_TN;
+    const int qtiles = (dims->Q + EMM_TQ - 1) / EMM_TQ;
+    const long nitems = (long)dims->R * qtiles;
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_mma_kernel<KT>, EMM_THREADS, smem);
+    if (occ < 1) occ = 1;
+    long workers = (long)nsm * occ / ntiles;
+    if (workers < 1) workers = 1;
+    if (workers > nitems) workers = nitems;
+    quad_embed_mma_kernel<KT><<<dim3(ntiles, (unsigned)workers), EMM_THREADS, smem, st>>>(*dims, *buf, flags);
+}
+
 }  // namespace
+
+// Returns false when K is outside this path (K + 1 > 40 latents); the caller then uses the CUDA-core kernel.
+bool svgpfa_try_quad_embed_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    const int KT = emm_kp(dims->K) / 8;
+    switch (KT) {
+        case 1: launch_emm<1>(dims, buf, flags, st); break;
+        case 2: launch_emm<2>(dims, buf, flags, st); break;
+        case 3: launch_emm<3>(dims, buf, flags, st); break;
+        case 4: launch_emm<4>(dims, buf, flags, st); break;
+        case 5: launch_emm<5>(dims, buf, flags, st); break;
+        default: return false;
+    }
+    return true;
+}
 
 // Returns false when the shape is outside this path (M > 32); the caller then uses the CUDA-core kernels.
 bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
