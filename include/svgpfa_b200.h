@@ -158,7 +158,8 @@ int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, v
  * expectedLogLikelihood.py:122-131; eLinkValues (R,Q,N) is never materialised. */
 int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 
-/* (iii) adjoint of svgpfa_quad_latent_fwd: A_q, abar_q and (if KERNEL|INDLOCS) dz_acc, dth_part.
+/* (iii) adjoint of svgpfa_quad_latent_fwd: A_q, abar_q and (if KERNEL|INDLOCS) dz_acc, dth_part (ADDED to: the
+ * caller zeroes dz_acc and dth_part once per evaluation, svgpfa_elbo_grad does).
  * The reference obtains these from torch.autograd (svEM.py:281). */
 int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 

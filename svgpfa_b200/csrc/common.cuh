@@ -39,6 +39,29 @@ __device__ __forceinline__ double svgpfa_exp_neg(double x, const double* __restr
     return __hiloint2double(__double2hiint(e) + ((n >> SVGPFA_EXP_TAB_BITS) << 20), __double2loint(e));
 }
 
+// Small-table variant for kernels that cannot spare 16 KB of shared memory: 64 entries (every 32nd of the big
+// table), degree-5 polynomial, 9 FP64 instructions.  Same clamp and error behaviour.
+__device__ __forceinline__ void svgpfa_load_exp_tab64(double* tab) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = svgpfa_exp2_tab_g[32 * i];
+}
+
+__device__ __forceinline__ double svgpfa_exp_neg64(double x, const double* __restrict__ tab) {
+    const unsigned hi = min((unsigned)__double2hiint(x), 0xC08617FFu);
+    x = __hiloint2double((int)hi, __double2loint(x));
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, SVGPFA_EXP_INV_L * 0.03125, MAGIC);      // 64 / ln2
+    const double nd = t - MAGIC;
+    const int n = __double2loint(t);
+    const double r = fma(nd, -32.0 * SVGPFA_EXP_L, x);               // ln2 / 64, |r| <= 5.5e-3
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double T = tab[n & 63];
+    const double e = fma(T * r, q, T);
+    return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
+}
+
 // Per-latent kernel constants derived from theta (kernels.py:33-46, 73-85).
 //   expquad : kappa = s2 exp(nh d^2),            nh = -0.5 / l^2
 //   periodic: kappa = s2 exp(nh sin^2(pi d/p)),  nh = -2 / l^2
@@ -105,6 +128,38 @@ __device__ __forceinline__ void kappa_grad(const KConst& kc, double delta, doubl
         const double q = s * s;
         const double s2x = 2.0 * s * c;
         kv = kc.s2 * exp(kc.nh * q);
+        dk_dd = kv * s2x * kc.dd;
+        dk_dt0 = kv * q * kc.dl;
+        dk_dt1 = kv * s2x * delta * kc.dp;
+    }
+}
+
+// Same as kappa_val / kappa_grad with the 64-entry table exp (tab in shared memory).
+__device__ __forceinline__ double kappa_val_t(const KConst& kc, double delta, const double* __restrict__ tab) {
+    double q;
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+        q = delta * delta;
+    } else {
+        const double s = sinpi(delta * kc.invp);
+        q = s * s;
+    }
+    return kc.s2 * svgpfa_exp_neg64(kc.nh * q, tab);
+}
+
+__device__ __forceinline__ void kappa_grad_t(const KConst& kc, double delta, const double* __restrict__ tab, double& kv,
+                                             double& dk_dd, double& dk_dt0, double& dk_dt1) {
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+        const double q = delta * delta;
+        kv = kc.s2 * svgpfa_exp_neg64(kc.nh * q, tab);
+        dk_dd = kv * delta * kc.dd;
+        dk_dt0 = kv * q * kc.dl;
+        dk_dt1 = 0.0;
+    } else {
+        double s, c;
+        sincospi(delta * kc.invp, &s, &c);
+        const double q = s * s;
+        const double s2x = 2.0 * s * c;
+        kv = kc.s2 * svgpfa_exp_neg64(kc.nh * q, tab);
         dk_dd = kv * s2x * kc.dd;
         dk_dt0 = kv * q * kc.dl;
         dk_dt1 = kv * s2x * delta * kc.dp;

@@ -148,6 +148,8 @@ __device__ __forceinline__ void for_my_blocks(const QLGeom& g, int pw, F f) {
 
 __global__ void __launch_bounds__(QL_THREADS) quad_latent_fwd_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
     extern __shared__ __align__(16) double sm[];
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab64(etab);
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const QLGeom g = ql_geom(ds.M);
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(QL_THREADS) quad_latent_fwd_kernel(svgpfa_dims
             const int q = q0 + col;
             const double t = (q < dm.Q) ? bf.tq[(size_t)r * dm.Q + q] : 0.0;
             for (int j = pw; j < MP; j += g.npw) {
-                const double kv = (q < dm.Q && j < M) ? kappa_val(kc, t - s.zs[j]) : 0.0;
+                const double kv = (q < dm.Q && j < M) ? kappa_val_t(kc, t - s.zs[j], etab) : 0.0;
                 s.ks[j * TQS + col] = kv;
                 mu = fma(kv, s.al[j], mu);
             }
@@ -217,6 +219,8 @@ template <bool BIG>
 __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab64(etab);
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const QLGeom g = ql_geom(ds.M);
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kerne
             if (pw == 0) { s.vb[col] = vbar; }
             int e = 0;
             for (int j = pw; j < MP; j += g.npw, ++e) {
-                const double kv = (valid && j < M) ? kappa_val(kc, t - s.zs[j]) : 0.0;
+                const double kv = (valid && j < M) ? kappa_val_t(kc, t - s.zs[j], etab) : 0.0;
                 s.ks[j * TQS + col] = kv;
                 const double sa = warp_sum(mbar * kv);
                 if (lane == e) ab_own += sa;
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kerne
                         if (valid && j < M) {
                             const double kbar = 2.0 * vbar * a[c] + mbar * s.al[j];
                             double kv, dkd, d0, d1;
-                            kappa_grad(kc, t - s.zs[j], kv, dkd, d0, d1);
+                            kappa_grad_t(kc, t - s.zs[j], etab, kv, dkd, d0, d1);
                             gz = -kbar * dkd;                        // d delta / d z = -1
                             th0 = fma(kbar, d0, th0);
                             th1 = fma(kbar, d1, th1);
@@ -414,15 +418,15 @@ __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kerne
             if (need_kz) sz += comb[(1 * g.nqs + q) * MP + tid];
         }
         bf.abar_q[vo + tid] = sa;
-        if (need_kz) bf.dz_acc[vo + tid] = sz;            // first writer of dz_acc (the spike kernel adds later)
+        if (need_kz) atomicAdd(bf.dz_acc + vo + tid, sz);  // zeroed by the caller; the spike kernel adds concurrently
     }
     if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
         const double s0 = block_sum(th0, red);
         const double s1 = block_sum(th1, red);
         if (tid == 0) {
             double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            dth[0] = s0;                                  // first writer of dth_part
-            if (ds.nth > 1) dth[1] = s1;
+            atomicAdd(dth, s0);                           // zeroed by the caller; the spike kernel adds concurrently
+            if (ds.nth > 1) atomicAdd(dth + 1, s1);
         }
     }
 }
@@ -577,10 +581,7 @@ __global__ void __launch_bounds__(EM_THREADS, 3) quad_embed_kernel(svgpfa_dims d
 extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
-    // forward: the CUDA-core kernel is still faster (2.48 vs 3.00 ms on the 2000-trial shard); SVGPFA_MMA_FWD=1 forces
-    // the tensor path for experiments
-    static const bool mma_fwd = getenv("SVGPFA_MMA_FWD") != nullptr;
-    if (mma_fwd && use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, 0, false, (cudaStream_t)stream)) {
+    if (use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, 0, false, (cudaStream_t)stream)) {
         SVGPFA_CHECK_LAUNCH("quad_latent_fwd (mma)");
         return SVGPFA_OK;
     }

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
+    __shared__ double etab[64];
+    svgpfa_load_exp_tab64(etab);
     const int r = blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const int M = ds.M;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                 const int j = 4 * ks + tg;
                 const double zj = zs[j];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) kf[ks][qt] = (v4[qt] && j < M) ? kappa_val(kc, t4[qt] - zj) : 0.0;
+                for (int qt = 0; qt < 4; ++qt) kf[ks][qt] = (v4[qt] && j < M) ? kappa_val_t(kc, t4[qt] - zj, etab) : 0.0;
             }
         }
         double mu4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                             const int ql = 8 * qt + 2 * tg + e;
                             const double kbar = 2.0 * vbs[ql] * w[jt][qt][e] + mbs[ql] * aj;
                             double kval, dkd, d0, d1;
-                            kappa_grad(kc, tt[ql] - zj, kval, dkd, d0, d1);
+                            kappa_grad_t(kc, tt[ql] - zj, etab, kval, dkd, d0, d1);
                             dzp[jt] = fma(-kbar, dkd, dzp[jt]);      // d delta / d z = -1
                             th0 = fma(kbar, d0, th0);
                             th1 = fma(kbar, d1, th1);
@@ -349,15 +351,15 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
             sz += t0p[(size_t)w * wstride + NTA * 64 + MP + tid];
         }
         bf.abar_q[vo + tid] = sa;
-        if (need_kz) bf.dz_acc[vo + tid] = sz;                       // first writer of dz_acc (the spike kernel adds later)
+        if (need_kz) atomicAdd(bf.dz_acc + vo + tid, sz);             // zeroed by the caller; the spike kernel adds concurrently
     }
     if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
         const double s0 = block_sum(th0, red);
         const double s1 = block_sum(th1, red);
         if (tid == 0) {
             double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            dth[0] = s0;                                             // first writer of dth_part
-            if (ds.nth > 1) dth[1] = s1;
+            atomicAdd(dth, s0);                                      // zeroed by the caller; the spike kernel adds concurrently
+            if (ds.nth > 1) atomicAdd(dth + 1, s1);
         }
     }
 }
