@@ -270,3 +270,41 @@ def test_ecm_driver_trajectory_matches_oracle_model():
     # the fitted parameters agree too
     for pg, pc in zip(gpu_model.getSVEmbeddingParams(), cpu_model.getSVEmbeddingParams()):
         assert rel_err(pg.detach().cpu().numpy(), pc.detach().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("cfg_name,R,N", [("config3", 6, 200), ("config4", 4, 300)])
+def test_baseline_config_shapes_against_oracle(cfg_name, R, N):
+    """BASELINE.json configs #3 (mixed ExponentialQuadratic / Periodic kernels, M=20, K=10) and #4 (heavy ragged
+    spikes up to 200 Hz, M=32, K=10) at their full per-trial shape on a few trials, against the oracle on the box."""
+    from oracle import svgpfa_oracle as orc
+    cfg = dict(synthetic.CONFIGS[cfg_name], R=R, N=N)
+    case = synthetic.make_case(cfg, seed=9)
+    ref = orc.elbo_and_grads(case, spike_var=False)
+    _, out = _eval_all(case)
+    assert abs(out["elbo"] - ref["elbo"]) <= ELBO_TOL * abs(ref["elbo"])
+    worst = max((rel_err(out[key], ref[key]), key) for key in _grad_keys(len(case["kernel_types"])))
+    assert worst[0] <= GRAD_TOL, worst
+
+
+def test_device_generator_and_ragged_balance():
+    """The device-side generator used by bench.py yields a valid problem (finite bound, gradients for every group)
+    for the heavy-ragged configuration, and spike-balanced trial blocks differ from equal-count blocks."""
+    from svgpfa_b200 import sharding
+    from svgpfa_b200.testing import model_from_case, set_requires_grad, grads_as_dict
+    cfg = dict(synthetic.CONFIGS["config4"], R=64)
+    case = synthetic.make_case_torch(cfg, torch.device("cuda"), seed=1)
+    model = model_from_case(case)
+    set_requires_grad(model)
+    v = model.eval()
+    v.backward()
+    assert np.isfinite(v.item())
+    for key, g in grads_as_dict(model).items():
+        assert g is not None and np.all(np.isfinite(g)), key
+    per_trial = case["spike_counts"].sum(1).cpu().numpy()
+    blocks = sharding.trial_blocks(per_trial, 4)
+    loads = [per_trial[a:b].sum() for a, b in blocks]
+    assert max(loads) <= per_trial.sum() / 4 + per_trial.max()
+    # sum over spike-balanced shards == whole problem
+    host = synthetic.case_to_numpy(case)
+    parts = [_eval_all(synthetic.slice_trials(host, a, b))[1]["elbo"] for a, b in blocks if b > a]
+    assert abs(sum(parts) - v.item()) <= 1e-11 * abs(v.item())
