@@ -134,6 +134,18 @@ __device__ __forceinline__ void kappa_grad(const KConst& kc, double delta, doubl
     }
 }
 
+// kappa with the 2048-entry table exp (tab in shared memory, svgpfa_load_exp_tab).
+__device__ __forceinline__ double kappa_val_big(const KConst& kc, double delta, const double* __restrict__ tab) {
+    double q;
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+        q = delta * delta;
+    } else {
+        const double s = sinpi(delta * kc.invp);
+        q = s * s;
+    }
+    return kc.s2 * svgpfa_exp_neg(kc.nh * q, tab);
+}
+
 // Same as kappa_val / kappa_grad with the 64-entry table exp (tab in shared memory).
 __device__ __forceinline__ double kappa_val_t(const KConst& kc, double delta, const double* __restrict__ tab) {
     double q;

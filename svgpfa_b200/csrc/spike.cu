@@ -239,14 +239,20 @@ constexpr int SM_THREADS = 256;
 
 __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm, svgpfa_buffers bf, int n_split) {
     extern __shared__ double sm[];
+    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
+    svgpfa_load_exp_tab(etab);
     double* zs = sm;                 // KM
-    double* as = zs + dm.KM;         // KM
+    double* as = zs + dm.KM;         // KM   scale^2 alpha
+    double* knh = as + dm.KM;        // K    kernel constants, computed once per CTA
+    double* kip = knh + dm.K;        // K    1/p (0 for the exponential-quadratic kernel)
     const int r = blockIdx.x / n_split, part = blockIdx.x - r * n_split;
     for (int k = 0; k < dm.K; ++k) {
         const svgpfa_latent_desc ds = bf.desc[k];
+        const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+        if (threadIdx.x == 0) { knh[k] = kc.nh; kip[k] = kc.type == SVGPFA_KERNEL_PERIODIC ? kc.invp : 0.0; }
         for (int j = threadIdx.x; j < ds.M; j += blockDim.x) {
             zs[ds.moff + j] = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + j];
-            as[ds.moff + j] = bf.alpha[(size_t)r * dm.KM + ds.moff + j];
+            as[ds.moff + j] = kc.s2 * bf.alpha[(size_t)r * dm.KM + ds.moff + j];
         }
     }
     __syncthreads();
@@ -254,10 +260,21 @@ __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm,
     for (int64_t s = s0 + (int64_t)part * blockDim.x + threadIdx.x; s < s1; s += (int64_t)n_split * blockDim.x) {
         const double t = bf.spike_t[s];
         for (int k = 0; k < dm.K; ++k) {
-            const svgpfa_latent_desc ds = bf.desc[k];
-            const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+            const int M = bf.desc[k].M, off = bf.desc[k].moff;
+            const double nh = knh[k], ip = kip[k];
             double mu = 0.0;
-            for (int j = 0; j < ds.M; ++j) mu = fma(kappa_val(kc, t - zs[ds.moff + j]), as[ds.moff + j], mu);
+            if (ip == 0.0) {
+#pragma unroll 4
+                for (int j = 0; j < M; ++j) {
+                    const double dl = t - zs[off + j];
+                    mu = fma(svgpfa_exp_neg(nh * (dl * dl), etab), as[off + j], mu);
+                }
+            } else {
+                for (int j = 0; j < M; ++j) {
+                    const double sn = sinpi((t - zs[off + j]) * ip);
+                    mu = fma(svgpfa_exp_neg(nh * (sn * sn), etab), as[off + j], mu);
+                }
+            }
             bf.mu_s[(size_t)s * dm.K + k] = mu;
         }
     }
@@ -368,7 +385,7 @@ extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_b
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     int n_split = (nsm * 8 + dims->R - 1) / dims->R;
     if (n_split < 1) n_split = 1;
-    const size_t smem = sizeof(double) * 2 * (size_t)dims->KM;
+    const size_t smem = sizeof(double) * (2 * (size_t)dims->KM + 2 * (size_t)dims->K);
     spike_means_kernel<<<dims->R * n_split, SM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, n_split);
     SVGPFA_CHECK_LAUNCH("spike_latent_means");
     return SVGPFA_OK;
