@@ -19,6 +19,29 @@ inline void stage_mark(int idx, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // FP64 pipe probes
 // ------------------------------------------------------------------------------------------
+// Are DFMA (FP64 pipe) and mma.m8n8k4.f64 (tensor DMMA sub-pipe) independent?  MIX = 8 DFMA + NM DMMA per iteration.
+template <int NF, int NM>
+__global__ void __launch_bounds__(256) mix_probe_kernel(long iters, double* out) {
+    const double av = 1.0 + 1e-9 * threadIdx.x, bv = 1.0 - 1e-9 * threadIdx.x;
+    double c[8][2], a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { c[e][0] = c[e][1] = 1e-3 * e; a[e] = 1e-3 * (threadIdx.x + 1) + 0.01 * e; }
+    const double m = 0.999999, k = 1e-9;
+    for (long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (e < NM)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[e][0]), "+d"(c[e][1]) : "d"(av), "d"(bv));
+            if (e < NF) a[e] = fma(a[e], m, k);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += c[e][0] + c[e][1] + a[e];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out) {
     __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
@@ -155,6 +178,11 @@ extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, do
         case 2: peak_probe_kernel<2><<<blocks, 256, 0, st>>>((long)iters, out); break;
         case 3: peak_probe_kernel<3><<<blocks, 256, 0, st>>>((long)iters, out); break;
         case 4: dmma_probe_kernel<<<blocks, 256, 0, st>>>((long)iters, out); break;
+        case 5: mix_probe_kernel<8, 1><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 1 DMMA
+        case 6: mix_probe_kernel<8, 2><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 2 DMMA
+        case 7: mix_probe_kernel<8, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA
+        case 8: mix_probe_kernel<0, 2><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 2 DMMA
+        case 9: mix_probe_kernel<8, 4><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 4 DMMA
         default: return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe kind", cudaSuccess);
     }
     SVGPFA_CHECK_LAUNCH("peak_probe");

@@ -30,6 +30,10 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
     return (size_t)2 * MP * ld + 2 * MP + (size_t)nw * ((bwd ? 2 : 1) * MP * QM_LDT + 3 * 32);
 }
 
+// Element-wise work (kernel evaluations, their derivatives, row sums) is written as ROLLED loops over a shared
+// tile with lane <-> point or lane <-> inducing point; only the mma sequences are unrolled.  (A first version kept
+// the kernel values in fragment registers and unrolled everything: 10 500 instructions, 23 % of the stall samples
+// were instruction-cache misses -- profiles/README.md.)
 template <int MT, bool BWD>
 __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
@@ -47,9 +51,10 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     double* Xs = Lis + MP * LD;                         // [MP][LD]  X
     double* al = Xs + MP * LD;                          // [MP]
     double* zs = al + MP;                               // [MP]
-    double* wbase = zs + MP + (size_t)warp * ((BWD ? 2 : 1) * MP * LDT + 3 * 32);
-    double* tileV = wbase;                              // [MP][LDT]
-    double* tileU = wbase + MP * LDT;                   // [MP][LDT]   (BWD only)
+    constexpr int WSTRIDE = (BWD ? 2 : 1) * MP * LDT + 3 * 32;
+    double* wbase = zs + MP + (size_t)warp * WSTRIDE;
+    double* tileV = wbase;                              // [MP][LDT]  V, later Li^T W
+    double* tileU = wbase + MP * LDT;                   // [MP][LDT]  K, later U, later W      (BWD only)
     double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the tile
     double* mbs = tt + 32;                              // [32] mubar
     double* vbs = mbs + 32;                             // [32] varbar
@@ -70,70 +75,69 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
         }
     }
     __syncthreads();
-    // persistent accumulators of the adjoint (BWD)
+    // persistent accumulators of the adjoint (BWD); lane j owns abar_j, dz_j
     constexpr int NTA = MT * (MT + 1) / 2;
     double accA[BWD ? NTA : 1][2];
-    double abp[BWD ? KS : 1], dzp[BWD ? MT : 1];
 #pragma unroll
     for (int e = 0; e < (BWD ? NTA : 1); ++e) accA[e][0] = accA[e][1] = 0.0;
-#pragma unroll
-    for (int e = 0; e < (BWD ? KS : 1); ++e) abp[e] = 0.0;
-#pragma unroll
-    for (int e = 0; e < (BWD ? MT : 1); ++e) dzp[e] = 0.0;
-    double th0 = 0.0, th1 = 0.0;
+    double ab_own = 0.0, dz_own = 0.0, th0 = 0.0, th1 = 0.0;
+    const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
     const int ntq = (dm.Q + 31) / 32;
     for (int qt0 = warp; qt0 < ntq; qt0 += nw) {
         const int qbase = qt0 * 32;
-        {   // stage the tile's nodes and statistic adjoints (lane <-> point)
-            const int q = qbase + lane;
-            const bool valid = q < dm.Q;
-            tt[lane] = valid ? bf.tq[(size_t)r * dm.Q + q] : 0.0;
-            if (BWD) {
-                double mbar = 0.0, vbar = 0.0;
-                if (valid) {
-                    const size_t o = ((size_t)r * dm.K + k) * dm.Q + q;
-                    for (int p = 0; p < dm.n_ntiles; ++p) {
-                        mbar += bf.mubar_part[p * part_stride + o];
-                        vbar += bf.varbar_part[p * part_stride + o];
-                    }
+        const int q_lane = qbase + lane;
+        const bool valid = q_lane < dm.Q;
+        const double t_lane = valid ? bf.tq[(size_t)r * dm.Q + q_lane] : 0.0;
+        tt[lane] = t_lane;
+        if (BWD) {
+            double mbar = 0.0, vbar = 0.0;
+            if (valid) {
+                const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;
+                for (int p = 0; p < dm.n_ntiles; ++p) {
+                    mbar += bf.mubar_part[p * part_stride + o];
+                    vbar += bf.varbar_part[p * part_stride + o];
                 }
-                mbs[lane] = mbar;
-                vbs[lane] = vbar;
             }
+            mbs[lane] = mbar;
+            vbs[lane] = vbar;
         }
-        __syncwarp();
-        // ---- kernel values in B-fragment layout: kf[ks][qt] = kappa(t[8 qt + g] - z[4 ks + tg])
-        double kf[KS][4];
-        {
+        // ---- kernel values.  BWD: lane <-> point, K[j][q] -> tileU (rolled loop; the tile feeds abar and the V
+        //      product).  FWD: directly in B-fragment registers kf[ks][qt] = kappa(t[8 qt + g] - z[4 ks + tg]) --
+        //      one tile less of shared memory, three resident CTAs per SM instead of two (measured 2.1 vs 2.8 ms).
+        double kf[BWD ? 1 : KS][4];
+        double mu4[4] = {0.0, 0.0, 0.0, 0.0};
+        if (BWD) {
+#pragma unroll 2
+            for (int j = 0; j < MP; ++j)
+                tileU[j * LDT + lane] = (valid && j < M) ? kappa_val_t(kc, t_lane - zs[j], etab) : 0.0;
+        } else {
+            __syncwarp();                                            // tt visible
             double t4[4];
             bool v4[4];
 #pragma unroll
             for (int qt = 0; qt < 4; ++qt) { t4[qt] = tt[8 * qt + g]; v4[qt] = (qbase + 8 * qt + g) < dm.Q; }
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
+            for (int ks = 0; ks < (BWD ? 1 : KS); ++ks) {
                 const int j = 4 * ks + tg;
-                const double zj = zs[j];
+                const double zj = zs[j], aj = al[j];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) kf[ks][qt] = (v4[qt] && j < M) ? kappa_val_t(kc, t4[qt] - zj, etab) : 0.0;
+                for (int qt = 0; qt < 4; ++qt) {
+                    kf[ks][qt] = (v4[qt] && j < M) ? kappa_val_t(kc, t4[qt] - zj, etab) : 0.0;
+                    mu4[qt] = fma(kf[ks][qt], aj, mu4[qt]);
+                }
             }
         }
-        double mu4[4] = {0.0, 0.0, 0.0, 0.0};
-        if (!BWD) {
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const double aj = al[4 * ks + tg];
-#pragma unroll
-                for (int qt = 0; qt < 4; ++qt) mu4[qt] = fma(kf[ks][qt], aj, mu4[qt]);
+        __syncwarp();
+        if (BWD && lane < MP) {
+            // abar_j += sum_q mubar_q K[j][q], lane <-> inducing point, skewed column order (conflict free)
+            double s_ = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+                const int q = (c + lane) & 31;
+                s_ = fma(mbs[q], tileU[lane * LDT + q], s_);
             }
-        } else {
-            double mb4[4];
-#pragma unroll
-            for (int qt = 0; qt < 4; ++qt) mb4[qt] = mbs[8 * qt + g];
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                for (int qt = 0; qt < 4; ++qt) abp[ks] = fma(mb4[qt], kf[ks][qt], abp[ks]);
+            ab_own += s_;
         }
         // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]
         double v[MT][4][2];
@@ -143,11 +147,14 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
             for (int qt = 0; qt < 4; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
+            double b[4];
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) b[qt] = BWD ? tileU[(4 * ks + tg) * LDT + 8 * qt + g] : kf[BWD ? 0 : ks][qt];
 #pragma unroll
             for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
                 const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, kf[ks][qt]);
+                for (int qt = 0; qt < 4; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, b[qt]);
             }
         }
         double vv[4][2];
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
             }
         }
         if (!BWD) {
-            // var = s2 - ||v||^2 + ||u||^2, mu = k . alpha : column sums over the 8 row groups / 4 k groups
+            // var = s2 - ||v||^2 + ||u||^2 : column sums over the 8 row groups
 #pragma unroll
             for (int qt = 0; qt < 4; ++qt) {
                 double d0 = -vv[qt][0], d1 = -vv[qt][1];
@@ -203,18 +210,19 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                     d0 += __shfl_xor_sync(0xffffffffu, d0, o);
                     d1 += __shfl_xor_sync(0xffffffffu, d1, o);
                 }
-                double m = mu4[qt];
-                m += __shfl_xor_sync(0xffffffffu, m, 1);
-                m += __shfl_xor_sync(0xffffffffu, m, 2);
                 if (g == 0) {                                      // lanes 0..3 hold columns 8 qt + 2 tg + {0,1}
                     const int q = qbase + 8 * qt + 2 * tg;
                     if (q < dm.Q) bf.var_q[((size_t)r * dm.Q + q) * dm.K + k] = kc.s2 + d0;
                     if (q + 1 < dm.Q) bf.var_q[((size_t)r * dm.Q + q + 1) * dm.K + k] = kc.s2 + d1;
                 }
-                if (tg == 0) {                                     // lanes with tg == 0 hold mu of point 8 qt + g
-                    const int q = qbase + 8 * qt + g;
-                    if (q < dm.Q) bf.mu_q[((size_t)r * dm.Q + q) * dm.K + k] = m;
-                }
+            }
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {                       // mu = k . alpha: sum over the 4 k groups
+                double m = mu4[qt];
+                m += __shfl_xor_sync(0xffffffffu, m, 1);
+                m += __shfl_xor_sync(0xffffffffu, m, 2);
+                const int q = qbase + 8 * qt + g;
+                if (tg == 0 && q < dm.Q) bf.mu_q[((size_t)r * dm.Q + q) * dm.K + k] = m;
             }
         } else {
             // ---- A += V diag(varbar) V^T over the 32 points: k-step = 4 points, A/B fragments from the V tile
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                         dmma(accA[it * (it + 1) / 2 + jt][0], accA[it * (it + 1) / 2 + jt][1], av[it] * sv, av[jt]);
             }
             if (need_kz) {
+                __syncwarp();                                        // K (tileU) fully consumed by every lane
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                     for (int qt = 0; qt < 4; ++qt)
                         *reinterpret_cast<double2*>(tileU + (8 * it + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[it][qt][0], w[it][qt][1]);
                 __syncwarp();
-                // ---- Kv = Li^T W, then kbar = 2 varbar Kv + mubar alpha and its products with dkappa
+                // ---- Kv = Li^T W -> tileV (V is no longer needed)
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
@@ -283,22 +292,25 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                         for (int qt = 0; qt < 4; ++qt) dmma(w[jt][qt][0], w[jt][qt][1], a, b[qt]);
                     }
                 }
+                __syncwarp();                                        // SYRK and the W initialisation are done with V
 #pragma unroll
-                for (int jt = 0; jt < MT; ++jt) {
-                    const int j = 8 * jt + g;
-                    const double zj = zs[j], aj = al[j];
+                for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
                     for (int qt = 0; qt < 4; ++qt)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int ql = 8 * qt + 2 * tg + e;
-                            const double kbar = 2.0 * vbs[ql] * w[jt][qt][e] + mbs[ql] * aj;
-                            double kval, dkd, d0, d1;
-                            kappa_grad_t(kc, tt[ql] - zj, etab, kval, dkd, d0, d1);
-                            dzp[jt] = fma(-kbar, dkd, dzp[jt]);      // d delta / d z = -1
-                            th0 = fma(kbar, d0, th0);
-                            th1 = fma(kbar, d1, th1);
-                        }
+                        *reinterpret_cast<double2*>(tileV + (8 * jt + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[jt][qt][0], w[jt][qt][1]);
+                __syncwarp();
+                // ---- kbar = 2 varbar Kv + mubar alpha and its products with dkappa; lane <-> inducing point
+                if (lane < M) {
+#pragma unroll 2
+                    for (int c = 0; c < 32; ++c) {
+                        const int q = (c + lane) & 31;
+                        const double kbar = 2.0 * vbs[q] * tileV[lane * LDT + q] + mbs[q] * aj_own;
+                        double kval, dkd, d0, d1;
+                        kappa_grad_t(kc, tt[q] - zj_own, etab, kval, dkd, d0, d1);
+                        dz_own = fma(-kbar, dkd, dz_own);            // d delta / d z = -1
+                        th0 = fma(kbar, d0, th0);
+                        th1 = fma(kbar, d1, th1);
+                    }
                 }
             }
         }
@@ -315,28 +327,16 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
             tileV[tl * 64 + g * 8 + 2 * tg] = accA[tl][0];
             tileV[tl * 64 + g * 8 + 2 * tg + 1] = accA[tl][1];
         }
-    // abar_j = sum over the 8 point groups; dz_j = sum over the 4 column groups
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        double s = abp[ks];
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (g == 0) tileV[NTA * 64 + 4 * ks + tg] = s;
-    }
-#pragma unroll
-    for (int jt = 0; jt < MT; ++jt) {
-        double s = dzp[jt];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (tg == 0) tileV[NTA * 64 + MP + 8 * jt + g] = s;
+    if (lane < MP) {
+        tileV[NTA * 64 + lane] = ab_own;
+        tileV[NTA * 64 + MP + lane] = dz_own;
     }
     __syncthreads();
-    const size_t wstride = 2 * MP * LDT + 3 * 32;
     const double* t0p = zs + MP;                                     // warp 0's region
     const size_t mo = (size_t)r * dm.MM + ds.mmoff;
     for (int idx = tid; idx < NTA * 64; idx += blockDim.x) {
         double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += t0p[(size_t)w * wstride + idx];
+        for (int w = 0; w < nw; ++w) s += t0p[(size_t)w * WSTRIDE + idx];
         const int tl = idx / 64, e = idx - tl * 64;
         int it = 0, rem = tl;
         while (rem >= it + 1) { rem -= it + 1; ++it; }
@@ -347,18 +347,18 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     if (tid < M) {
         double sa = 0.0, sz = 0.0;
         for (int w = 0; w < nw; ++w) {
-            sa += t0p[(size_t)w * wstride + NTA * 64 + tid];
-            sz += t0p[(size_t)w * wstride + NTA * 64 + MP + tid];
+            sa += t0p[(size_t)w * WSTRIDE + NTA * 64 + tid];
+            sz += t0p[(size_t)w * WSTRIDE + NTA * 64 + MP + tid];
         }
         bf.abar_q[vo + tid] = sa;
-        if (need_kz) atomicAdd(bf.dz_acc + vo + tid, sz);             // zeroed by the caller; the spike kernel adds concurrently
+        if (need_kz) atomicAdd(bf.dz_acc + vo + tid, sz);             // zeroed by the caller; the spike kernel adds too
     }
     if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
         const double s0 = block_sum(th0, red);
         const double s1 = block_sum(th1, red);
         if (tid == 0) {
             double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            atomicAdd(dth, s0);                                      // zeroed by the caller; the spike kernel adds concurrently
+            atomicAdd(dth, s0);                                      // zeroed by the caller; the spike kernel adds too
             if (ds.nth > 1) atomicAdd(dth + 1, s1);
         }
     }
