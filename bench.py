@@ -393,6 +393,15 @@ def run_b200(args):
     total_equiv = (cnt["F_setup"] + cnt["F_quad"] + cnt["F_embed"] + 2.0 * slots
                    + cnt["N_exp_other"] * 2.0 * 7.0)
     roofline["whole_step_frac"] = total_equiv / (ms_step * 1e-3) / 1e12 / peak_tf
+    try:        # DRAM traffic of the launch from the committed ncu --set full capture of the same configuration
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_spike_traffic.json"))).get(args.config)
+        if tr and tr["trials"] == r1 - r0:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_note"] = ("ncu dram bytes per launch; algorithmic minimum 8 B x spikes = %.2e: every spike "
+                                        "is re-read by the ceil(K*M/128) CTAs that cover the (latent, inducing point) "
+                                        "pairs of its trial; 57 GB/s, far from the HBM roof" % (8.0 * S_local))
+    except Exception:
+        pass
 
     cpu = None
     if not args.no_cpu and world == 1:
