@@ -231,6 +231,8 @@ int svgpfa_set_stage_events(void** events);
 int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, void* stream);
 /* Test hook: y_fast[i] = the library's exp for non-positive arguments, y_ref[i] = libdevice exp(x[i]). */
 int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream);
+/* Test hook: y[i] = 2^(-min(w2[i], 2.61e5) / 256), the pre-scaled exponential of the spike kernel (w2 >= 0). */
+int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ SYMBOLS = {
     "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),
     "svgpfa_peak_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "svgpfa_exp_neg_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgpfa_exp2m_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 STAGES = ("kzz_chol", "indpoints_fwd", "quad_latent_fwd", "quad_embed", "quad_latent_bwd", "spike_fwd_bwd",
           "indpoints_bwd", "finalize")

@@ -42,6 +42,87 @@ __global__ void __launch_bounds__(256) mix_probe_kernel(long iters, double* out)
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Issue-model probes: 8 independent FP64 chains per thread with ALL operands in distinct registers (the DFMA probe
+// above has two constant operands), optionally interleaved with NI integer instructions or one shared-memory load
+// per FP64 instruction.  OP: 0 = DFMA (3 register operands), 1 = DADD, 2 = DMUL.
+template <int OP, int NI, int LDS>
+__global__ void __launch_bounds__(256) issue_probe_kernel(long iters, double* out) {
+    __shared__ double sm[256];
+    sm[threadIdx.x] = 1e-9 * threadIdx.x;
+    __syncthreads();
+    double a[8], b[8], c[8];
+    int k[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        a[e] = out[(threadIdx.x + e) & 255] * 1e-300 + 1e-3 * (threadIdx.x + 1) + 0.01 * e;
+        b[e] = 0.999999 - 1e-9 * e + out[(threadIdx.x + 8 + e) & 255] * 1e-300;
+        c[e] = 1e-9 * (e + 1) + out[(threadIdx.x + 16 + e) & 255] * 1e-300;
+        k[e] = threadIdx.x + e;
+    }
+    for (long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (OP == 0) a[e] = fma(a[e], b[e], c[e]);
+            else if (OP == 1) a[e] = a[e] + c[e];
+            else a[e] = a[e] * b[e];
+            if (NI >= 1) k[e] = k[e] * 3 + 1;
+            if (NI >= 2) k[e] = (k[e] >> 3) ^ k[e];
+            if (NI >= 3) k[e] = k[e] * 5 + 7;
+            if (LDS) c[e] += sm[(k[e] + (int)i) & 255] * 0.0;   // 1 LDS (+1 DFMA) per step
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += a[e] + (double)k[e] + c[e];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// The spike kernel's evaluation sequence in isolation (no segments, no staging): per step 4 evaluations of
+// w = t sc + zs, kappa = 2^(-w^2/256), pn += kappa, p1 += kappa w, p2 += kappa w^2 with t read from shared memory.
+// MODE 0: as in the kernel; 1: without the moment accumulations (KGRAD = false); 2: table entry replaced by a constant
+// (no table LDS); 3: without the spike-time LDS.
+template <int MODE>
+__global__ void __maxnreg__(128) eval_probe_kernel(long iters, double* out) {
+    __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
+    __shared__ double ts[1024];
+    svgpfa_load_exp2m_tab(tab);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) ts[i] = 1e-3 * i;
+    __syncthreads();
+    const unsigned lane_tab = svgpfa_exp2m_lane_tab(tab);
+    const double sc = 13.0 + out[threadIdx.x] * 1e-300, zs = -0.37 * (threadIdx.x & 31) - 1e-3 * (threadIdx.x >> 5);
+    double pn = 0.0, p1 = 0.0, p2 = 0.0;
+    for (long i = 0; i < iters; ++i) {
+        const double* tp = ts + ((i * 4) & 1020);
+        double t[4], w[4], w2[4], kv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = MODE == 3 ? 1e-3 * e + pn * 1e-300 : tp[e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { w[e] = fma(t[e], sc, zs); w2[e] = w[e] * w[e]; }
+        if (MODE == 2) {
+            const double MAGIC = 6755399441055744.0, L = SVGPFA_EXP2M_L;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double tt = MAGIC - w2[e];
+                const double u = w2[e] + (tt - MAGIC);
+                const int n = __double2loint(tt);
+                double q = fma(u, L * L * L * L / 24.0, -L * L * L / 6.0);
+                q = fma(u, q, L * L / 2.0);
+                q = fma(-u, q, L);
+                const double T = __hiloint2double(0x3ff00000 + (n << 12), n & 255);
+                kv[e] = fma(-(T * u), q, T);
+            }
+        } else {
+            svgpfa_exp2m_n<4>(w2, lane_tab, kv);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            pn += kv[e];
+            if (MODE != 1) { p1 = fma(kv[e], w[e], p1); p2 = fma(kv[e], w2[e], p2); }
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = pn + p1 + p2;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out) {
     __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
@@ -93,6 +174,15 @@ __global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n)
         yf[i] = svgpfa_exp_neg(x[i], etab);
         yr[i] = exp(x[i]);
     }
+}
+
+__global__ void exp2m_eval_kernel(const double* w2, double* y, long n) {
+    __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
+    svgpfa_load_exp2m_tab(tab);
+    __syncthreads();
+    const unsigned lane_tab = svgpfa_exp2m_lane_tab(tab);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = svgpfa_exp2m(svgpfa_exp2m_clamp(w2[i]), lane_tab);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -183,6 +273,17 @@ extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, do
         case 7: mix_probe_kernel<8, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA
         case 8: mix_probe_kernel<0, 2><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 2 DMMA
         case 9: mix_probe_kernel<8, 4><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 4 DMMA
+        case 10: issue_probe_kernel<0, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA, 3 registers
+        case 11: issue_probe_kernel<1, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DADD
+        case 12: issue_probe_kernel<2, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DMUL
+        case 13: issue_probe_kernel<0, 1, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 1 int
+        case 14: issue_probe_kernel<0, 2, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 2 int
+        case 15: issue_probe_kernel<0, 3, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 3 int
+        case 16: issue_probe_kernel<0, 1, 1><<<blocks, 256, 0, st>>>((long)iters, out); break;  // 2 DFMA + 1 int + 1 LDS (+addr)
+        case 20: eval_probe_kernel<0><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 21: eval_probe_kernel<1><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 22: eval_probe_kernel<2><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 23: eval_probe_kernel<3><<<blocks, 128, 0, st>>>((long)iters, out); break;
         default: return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe kind", cudaSuccess);
     }
     SVGPFA_CHECK_LAUNCH("peak_probe");
@@ -195,6 +296,14 @@ extern "C" int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_re
     if (n == 0) return SVGPFA_OK;
     exp_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(x, y_fast, y_ref, (long)n);
     SVGPFA_CHECK_LAUNCH("exp_neg_eval");
+    return SVGPFA_OK;
+}
+
+extern "C" int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream) {
+    if (!w2 || !y || n < 0) return svgpfa_set_error(SVGPFA_E_ARG, "exp2m_eval", cudaSuccess);
+    if (n == 0) return SVGPFA_OK;
+    exp2m_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(w2, y, (long)n);
+    SVGPFA_CHECK_LAUNCH("exp2m_eval");
     return SVGPFA_OK;
 }
 

@@ -39,6 +39,114 @@ __device__ __forceinline__ double svgpfa_exp_neg(double x, const double* __restr
     return __hiloint2double(__double2hiint(e) + ((n >> SVGPFA_EXP_TAB_BITS) << 20), __double2loint(e));
 }
 
+// 2^(-w2 / 256) for 0 <= w2 <= SVGPFA_EXP2M_LIMIT, for callers that work in pre-scaled coordinates (argument already
+// in units of 1/256 octave, e.g. w2 = d^2 * 256 / (2 ln2 l^2)); no argument scaling and no clamp per evaluation.
+//   n = rint(-w2), u = w2 + n in [-1/2, 1/2] (exact), 2^(-w2/256) = 2^(n>>8) T[n & 255] exp(-u ln2/256), degree 4.
+// The 2048-entry table of svgpfa_exp_neg costs ~6 shared-memory wavefronts per warp lookup (random 8-byte gathers:
+// ncu showed the LSU data pipe 80 % busy in the spike kernel).  Here the table has 256 entries, each REPLICATED 16
+// times (32 KB): lane l reads replica l & 15, so the 16 lanes of a half-warp always hit 16 different bank pairs --
+// 2 wavefronts, the minimum for a 64-bit load -- at the price of one more polynomial term: 8 FP64 + 4 other
+// instructions.  The copy in shared memory has j << 12 subtracted from the high word of entry j, so that ONE
+// integer add of n << 12 both restores the entry and applies the binary exponent n >> 8.
+// Relative error <= 3.5e-16 (host check against long-double exp2; tests/test_gpu_kernels.py::test_exp2m_accuracy).
+// Above the limit the exponent field would wrap: callers clamp (svgpfa_exp2m_clamp) or prove the bound.
+#define SVGPFA_EXP2M_BITS 8
+#define SVGPFA_EXP2M_REP 16
+#define SVGPFA_EXP2M_TAB_BYTES (8 * SVGPFA_EXP2M_REP << SVGPFA_EXP2M_BITS)        /* 32 KB */
+#define SVGPFA_EXP2M_INV_L (SVGPFA_EXP_INV_L * 0.125)                              /* 256 / ln2 */
+#define SVGPFA_EXP2M_L (SVGPFA_EXP_L * 8.0)                                        /* ln2 / 256 */
+#define SVGPFA_EXP2M_LIMIT 2.61e5            /* (n >> 8) >= -1020: the result stays a normal number */
+
+// tab: SVGPFA_EXP2M_TAB_BYTES of shared memory, [entry][replica]
+__device__ __forceinline__ void svgpfa_load_exp2m_tab(double* tab) {
+    for (int i = threadIdx.x; i < (SVGPFA_EXP2M_REP << SVGPFA_EXP2M_BITS); i += blockDim.x) {
+        const int j = i / SVGPFA_EXP2M_REP;
+        const double v = svgpfa_exp2_tab_g[j << (SVGPFA_EXP_TAB_BITS - SVGPFA_EXP2M_BITS)];
+        tab[i] = __hiloint2double(__double2hiint(v) - (j << (20 - SVGPFA_EXP2M_BITS)), __double2loint(v));
+    }
+}
+
+// 32-bit shared-window address of this lane's replica of entry 0
+__device__ __forceinline__ unsigned svgpfa_exp2m_lane_tab(const double* tab) {
+    return (unsigned)__cvta_generic_to_shared(tab) + 8u * (threadIdx.x & (SVGPFA_EXP2M_REP - 1));
+}
+
+__device__ __forceinline__ double svgpfa_exp2m(double w2, unsigned lane_tab) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double L = SVGPFA_EXP2M_L;
+    const double C1 = L, C2 = L * L / 2.0, C3 = L * L * L / 6.0, C4 = L * L * L * L / 24.0;
+    const double t = MAGIC - w2;
+    const double nd = t - MAGIC;
+    const double u = w2 + nd;
+    const int n = __double2loint(t);
+    double q = fma(u, C4, -C3);
+    q = fma(u, q, C2);
+    q = fma(-u, q, C1);                                       // exp(-uL) = 1 - u q
+    // entry address = lane_tab + (n & 255) * 128 (8 B * 16 replicas): one LOP3 and one IMAD
+    double Tb;
+    asm("{\n\t.reg .u32 i, a;\n\tand.b32 i, %1, 255;\n\tmad.lo.u32 a, i, 128, %2;\n\tld.shared.f64 %0, [a];\n\t}"
+        : "=d"(Tb) : "r"(n), "r"(lane_tab));
+    const double T = __hiloint2double(__double2hiint(Tb) + (n << (20 - SVGPFA_EXP2M_BITS)), __double2loint(Tb));
+    // T * (1 - u q): two instructions with two register operands each (a DFMA with three distinct register operands
+    // costs ~3.5 issue cycles on this part against 2, tools/probe_issue.py)
+    return T * fma(-u, q, 1.0);
+}
+
+// NE independent evaluations of svgpfa_exp2m written stage by stage.  The opaque asm statements between the stages
+// keep the compiler from serialising the NE dependency chains (it otherwise emits one chain after the other to save
+// registers, and the FP64 latency of ~10 cycles per dependent instruction is then exposed; ncu: 43 % "wait" stalls).
+#define SVGPFA_PIN4(x) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]))
+template <int NE>
+__device__ __forceinline__ void svgpfa_pin(double (&x)[NE]) {
+    if constexpr (NE == 4) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]));
+    else if constexpr (NE == 2) asm volatile("" : "+d"(x[0]), "+d"(x[1]));
+    else asm volatile("" : "+d"(x[0]));
+}
+
+template <int NE>
+__device__ __forceinline__ void svgpfa_exp2m_n(const double (&w2)[NE], unsigned lane_tab, double (&out)[NE]) {
+    const double MAGIC = 6755399441055744.0;
+    const double L = SVGPFA_EXP2M_L;
+    const double C1 = L, C2 = L * L / 2.0, C3 = L * L * L / 6.0, C4 = L * L * L * L / 24.0;
+    double t[NE], u[NE], q[NE], T[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) t[e] = MAGIC - w2[e];
+    svgpfa_pin(t);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int n = __double2loint(t[e]);
+        double Tb;
+        asm("{\n\t.reg .u32 i, a;\n\tand.b32 i, %1, 255;\n\tmad.lo.u32 a, i, 128, %2;\n\tld.shared.f64 %0, [a];\n\t}"
+            : "=d"(Tb) : "r"(n), "r"(lane_tab));
+        T[e] = __hiloint2double(__double2hiint(Tb) + (n << (20 - SVGPFA_EXP2M_BITS)), __double2loint(Tb));
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) u[e] = w2[e] + (t[e] - MAGIC);
+    svgpfa_pin(u);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(u[e], C4, -C3);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(u[e], q[e], C2);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], C1);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], 1.0);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) out[e] = T[e] * q[e];
+    svgpfa_pin(out);
+}
+
+// integer-pipe clamp of a non-negative double to SVGPFA_EXP2M_LIMIT (high words of non-negative doubles order
+// like the values)
+__device__ __forceinline__ double svgpfa_exp2m_clamp(double w2) {
+    const unsigned hi = min((unsigned)__double2hiint(w2), 0x410FDC3Fu);      // 0x410FDC40 00000000 = 2.61e5
+    return __hiloint2double((int)hi, __double2loint(w2));
+}
+
 // Small-table variant for kernels that cannot spare 16 KB of shared memory: 64 entries (every 32nd of the big
 // table), degree-5 polynomial, 9 FP64 instructions.  Same clamp and error behaviour.
 __device__ __forceinline__ void svgpfa_load_exp_tab64(double* tab) {

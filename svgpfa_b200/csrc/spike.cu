@@ -235,6 +235,249 @@ __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa
 }
 
 // ------------------------------------------------------------------------------------------
+// spike_tile_kernel: the same term with the spikes of the CTA's neuron range staged through SHARED memory and a
+// leaner inner loop (13 FP64 + ~5 other instructions per (spike, inducing point)).  What the ncu captures of the
+// kernel above showed, and what this one does about it:
+//   * its 2048-entry exp table cost ~6 shared-memory wavefronts per warp lookup (random 8-byte gathers; LSU data
+//     pipe 80 % busy)  ->  svgpfa_exp2m: 256 entries x 16 replicas, conflict-free by construction (common.cuh);
+//   * the warps of a CTA own 128 consecutive pairs of ONE trial and walk the same spikes, so a tile of ST_TILE spike
+//     times is loaded once per CTA (coalesced), re-based to the tile's first spike (t' = t - t0: small magnitudes, so
+//     the scaled difference below keeps full relative accuracy) and read with warp-uniform LDS; the segment ends
+//     and the embedding weight are fetched one segment ahead;
+//   * exponential-quadratic pairs use pre-scaled coordinates: w = t' sc - (z - t0) sc with
+//     sc = sqrt(256 / (2 ln2)) / l, so that kappa = 2^(-w^2 / 256) and the moments are taken in w:
+//     sum kappa, sum kappa w, sum kappa w^2, rescaled by 1/sc, 1/sc^2 once per lane;
+//   * the range clamp of the exponent is decided per tile from the tile's [min, max] spike time (warp-uniform
+//     branch to a clamping copy of the loop), not per evaluation.
+// Where the time goes now (tools/probe_eval.py, tools/probe_issue.py): the evaluation sequence ALONE, without
+// segments or staging, runs at 35.6 cycles per warp evaluation per SM sub-partition -- an FP64 instruction costs
+// max(2, number of distinct register operands) issue cycles (DFMA with three register operands: 3.0-3.7) and the
+// integer/LDS instructions are not hidden -- and the kernel reaches 44 cycles (81 % of that).  More pairs per lane
+// (NP = 2, 4) amortise the per-segment work but were measured slower (register pressure, profiles/README.md).
+// NP > 1 requires every M_k to be a multiple of NP (all pairs of a lane then share the latent).
+// Register budget: __maxnreg__ instead of a min-blocks launch bound -- with a min-blocks hint ptxas assumes the
+// resident warps hide latency and emits the evaluations of an iteration as one dependency chain after the other.
+constexpr int ST_TILE = 1024;
+constexpr int ST_MAX_WPB = 8;
+constexpr unsigned ST_SMEM = SVGPFA_EXP2M_TAB_BYTES + 8 * (ST_TILE + 2 * ST_MAX_WPB);
+
+// U spikes x NP pairs = NE independent evaluations, stage by stage (svgpfa_exp2m_n)
+template <bool KGRAD, bool CLAMP, int U, int NP>
+__device__ __forceinline__ void eq_eval_n(const double (&t)[U], double sc, const double (&zs)[NP], unsigned etab,
+                                          double (&pn)[NP], double (&p1)[NP], double (&p2)[NP]) {
+    constexpr int NE = U * NP;
+    double w[NE], w2[NE], wc[NE], kv[NE];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) w[u * NP + p] = fma(t[u], sc, zs[p]);
+    svgpfa_pin(w);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) w2[e] = w[e] * w[e];
+    svgpfa_pin(w2);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) wc[e] = CLAMP ? svgpfa_exp2m_clamp(w2[e]) : w2[e];
+    svgpfa_exp2m_n<NE>(wc, etab, kv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int e = u * NP + p;
+            pn[p] += kv[e];
+            if (KGRAD) {
+                p1[p] = fma(kv[e], w[e], p1[p]);
+                p2[p] = fma(kv[e], w2[e], p2[p]);
+            }
+        }
+    }
+}
+
+// cnt spikes (warp-uniform shared-memory reads) against the NP pairs of the lane; 4 / NP spikes per iteration
+template <bool KGRAD, bool CLAMP, int NP>
+__device__ __forceinline__ void eq_run(const double* __restrict__ tp, int cnt, double sc, const double (&zs)[NP],
+                                       unsigned etab, double (&pn)[NP], double (&p1)[NP], double (&p2)[NP]) {
+    constexpr int U = 4 / NP;
+    const double* const pe = tp + (cnt - cnt % U);
+#pragma unroll 1
+    for (; tp != pe; tp += U) {
+        double t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = tp[u];
+        eq_eval_n<KGRAD, CLAMP, U, NP>(t, sc, zs, etab, pn, p1, p2);
+    }
+    if (U == 4 && (cnt & 2)) {
+        const double t[2] = {tp[0], tp[1]};
+        eq_eval_n<KGRAD, CLAMP, 2, NP>(t, sc, zs, etab, pn, p1, p2);
+        tp += 2;
+    }
+    if (U >= 2 && (cnt & 1)) {
+        const double t[1] = {tp[0]};
+        eq_eval_n<KGRAD, CLAMP, 1, NP>(t, sc, zs, etab, pn, p1, p2);
+    }
+}
+
+// periodic pairs: w = sin(pi d/p) sc with sc = sqrt(256 * 2 / ln2) / l;  p1 += kappa sin(2 pi d/p),
+// p2 += kappa w^2 (rescaled by 1/sc^2 at the end), p3 += kappa sin(2 pi d/p) d
+template <bool KGRAD, int NP>
+__device__ __forceinline__ void per_run(const double* __restrict__ tp, int cnt, double sc, const double (&zc)[NP],
+                                        double invp, unsigned etab, double (&pn)[NP], double (&p1)[NP],
+                                        double (&p2)[NP], double (&p3)[NP]) {
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+        const double t = tp[i];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double dl = t - zc[p];
+            double sn, cs;
+            sincospi(dl * invp, &sn, &cs);
+            const double w = sn * sc;
+            const double w2 = w * w;
+            const double kv = svgpfa_exp2m(svgpfa_exp2m_clamp(w2), etab);
+            pn[p] += kv;
+            if (KGRAD) {
+                const double ww = kv * (2.0 * sn * cs);
+                p1[p] += ww;
+                p2[p] = fma(kv, w2, p2[p]);
+                p3[p] = fma(ww, dl, p3[p]);
+            }
+        }
+    }
+}
+
+template <bool KGRAD, int NP, int MAXT, int MAXR>
+__global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
+                                                                int n_chunks, int chunk) {
+    extern __shared__ __align__(16) double st_smem[];       // ST_SMEM bytes: table | spike tile | min/max scratch
+    double* ts = st_smem + SVGPFA_EXP2M_TAB_BYTES / 8;
+    double* red = ts + ST_TILE;
+    svgpfa_load_exp2m_tab(st_smem);
+    const unsigned etab = svgpfa_exp2m_lane_tab(st_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int r = blockIdx.x / n_chunks, nc = blockIdx.x - r * n_chunks;
+    const int grp = blockIdx.y * wpb + warp;
+    // a warp past the last pair still takes part in the staging and the barriers; its lanes are inactive
+    const PairInfo pi = pair_info(dm, bf, (grp * 32 + lane) * NP, lane);       // first pair of the lane
+    const svgpfa_latent_desc ds = bf.desc[pi.k];
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi.k);
+    const bool per = kc.type == SVGPFA_KERNEL_PERIODIC;
+    const double sc = sqrt(-kc.nh * SVGPFA_EXP2M_INV_L);
+    double z[NP], a[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int l = pi.active ? pi.li + p : dm.KM - 1;
+        z[p] = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + (l - ds.moff)];
+        a[p] = pi.active ? kc.s2 * bf.alpha[(size_t)r * dm.KM + l] : 0.0;     // scale^2 alpha_j
+    }
+    const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
+    const bool warp_live = grp * 32 * NP < dm.KM;
+    const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
+    const int64_t* __restrict__ seg = bf.seg_off + (size_t)r * dm.N;
+    const double* __restrict__ st = bf.spike_t;
+    const double* __restrict__ Ck = bf.C + pi.k;
+    double* gC = bf.shared + SVGPFA_SHARED_HDR + pi.k;
+    const int64_t S0 = seg[nb], S1 = seg[ne];
+    double abar[NP], dz[NP], d0[NP], d1[NP], pn[NP], p1[NP], p2[NP], p3[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) abar[p] = dz[p] = d0[p] = d1[p] = pn[p] = p1[p] = p2[p] = p3[p] = 0.0;
+    // segment walk: n = current neuron, seg_end = end of its segment, seg_nxt = end of the next one (loaded one
+    // segment ahead so that its latency is hidden behind a segment's worth of arithmetic)
+    int n = nb;
+    int64_t seg_end = seg[nb + 1], pos = S0;
+    int64_t seg_nxt = seg[min(nb + 2, ne)];
+    double c = Ck[(size_t)n * dm.K];
+    for (int64_t tile0 = S0; tile0 < S1; tile0 += ST_TILE) {
+        const int len = (int)min((int64_t)ST_TILE, S1 - tile0);
+        __syncthreads();                       // the previous tile has been consumed (and the table is loaded)
+        const double t0 = st[tile0];
+        double lo = 0.0, hi = 0.0;             // t' of the tile's first spike is 0
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            const double v = st[tile0 + i] - t0;
+            ts[i] = v;
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { red[warp] = lo; red[ST_MAX_WPB + warp] = hi; }
+        __syncthreads();
+        if (!warp_live) continue;
+        for (int w = 0; w < wpb; ++w) { lo = fmin(lo, red[w]); hi = fmax(hi, red[ST_MAX_WPB + w]); }
+        double zc[NP], zs[NP];
+        bool over = false;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            zc[p] = z[p] - t0;
+            zs[p] = -zc[p] * sc;
+            const double wm = fmax(fabs(fma(lo, sc, zs[p])), fabs(fma(hi, sc, zs[p])));
+            over |= !(wm * wm < SVGPFA_EXP2M_LIMIT);
+        }
+        const bool clamp = __any_sync(0xffffffffu, !per && over);
+        const int64_t tile1 = tile0 + len;
+        while (pos < tile1) {
+            while (seg_end <= pos) {                                       // next non-empty segment (pos < S1 here)
+                ++n;
+                seg_end = seg_nxt;
+                seg_nxt = seg[min(n + 2, ne)];
+                c = Ck[(size_t)n * dm.K];
+            }
+            const int64_t e = min(seg_end, tile1);
+            const int cnt = (int)(e - pos);
+            const double* tp = ts + (int)(pos - tile0);
+            if (per) per_run<KGRAD, NP>(tp, cnt, sc, zc, kc.invp, etab, pn, p1, p2, p3);
+            else if (clamp) eq_run<KGRAD, true, NP>(tp, cnt, sc, zs, etab, pn, p1, p2);
+            else eq_run<KGRAD, false, NP>(tp, cnt, sc, zs, etab, pn, p1, p2);
+            __syncwarp();
+            pos = e;
+            if (pos == seg_end) {                                          // segment (r, n) complete
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    abar[p] = fma(c, pn[p], abar[p]);
+                    if (KGRAD) {
+                        dz[p] = fma(c, p1[p], dz[p]);
+                        d0[p] = fma(c, p2[p], d0[p]);
+                        d1[p] = fma(c, p3[p], d1[p]);
+                    }
+                    v = fma(pn[p], a[p], v);
+                    pn[p] = p1[p] = p2[p] = p3[p] = 0.0;
+                }
+                if (need_emb) {
+                    v = seg_sum(v, pi.same);
+                    if (pi.head) atomicAdd(gC + (size_t)n * dm.K, v);
+                }
+            }
+        }
+    }
+    if (!warp_live) return;
+    const double isc = 1.0 / sc;
+    double t0s = 0.0, t1s = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        if (pi.active) {
+            atomicAdd(bf.abar_spk + (size_t)r * dm.KM + pi.li + p, kc.s2 * abar[p]);
+            // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin 2 pi d/p) * dd
+            if (KGRAD && (flags & SVGPFA_GRAD_INDLOCS))
+                atomicAdd(bf.dz_acc + (size_t)r * dm.KM + pi.li + p, -a[p] * kc.dd * (per ? dz[p] : dz[p] * isc));
+            // dkappa/dtheta0 = kappa (d^2 | sin^2) dl;  periodic: dkappa/dtheta1 = kappa sin(2 pi d/p) d dp
+            t0s = fma(a[p] * kc.dl, d0[p] * isc * isc, t0s);
+            t1s = fma(a[p] * kc.dp, d1[p], t1s);
+        }
+    }
+    if (KGRAD && (flags & SVGPFA_GRAD_KERNEL)) {
+        const double t0 = seg_sum(t0s, pi.same);
+        const double t1 = seg_sum(t1s, pi.same);
+        if (pi.head) {
+            double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
+            atomicAdd(dth, t0);
+            if (ds.nth > 1) atomicAdd(dth + 1, t1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int SM_THREADS = 256;
 
 __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm, svgpfa_buffers bf, int n_split) {
@@ -322,23 +565,34 @@ __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm
 
 }  // namespace
 
-template <bool KGRAD, int UNROLL, int MINB, int NP>
-static void launch_spike(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st, int nsm) {
-    const int per_warp = 32 * NP;
-    const int LG = (dims->KM + per_warp - 1) / per_warp;
-    const int gy = (LG + SP_WPB - 1) / SP_WPB;
-    // enough warps to fill the machine a few times over: split every trial's neurons into chunks
-    const long target_warps = (long)nsm * 64 * 4;
+// Grid of the spike kernels: warps of 32 * np pairs, wpb warps per CTA (the value in [min_wpb, max_wpb] that leaves
+// the fewest idle warps), and enough CTAs to fill the machine a few times over (every trial's neurons are split into
+// n_chunks ranges when R alone does not provide them).
+static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, int max_wpb, dim3* grid, int* wpb_out,
+                       int* n_chunks_out, int* chunk_out) {
+    const int LG = (dims->KM + 32 * np - 1) / (32 * np);
+    int wpb = LG < min_wpb ? LG : min_wpb, best = 1 << 30;
+    for (int w = min_wpb; w <= max_wpb && LG >= min_wpb; ++w) {
+        const int waste = (LG + w - 1) / w * w - LG;
+        if (waste < best) { best = waste; wpb = w; }
+    }
+    const int gy = (LG + wpb - 1) / wpb;
+    const long target_warps = (long)nsm * 64 * 4 / np;
     long n_chunks = (target_warps + (long)dims->R * LG - 1) / ((long)dims->R * LG);
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > dims->N) n_chunks = dims->N;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
-    const dim3 grid((unsigned)(dims->R * n_chunks), gy);
-    spike_fwd_bwd_kernel<KGRAD, UNROLL, MINB, NP><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, (int)n_chunks, chunk);
+    *grid = dim3((unsigned)(dims->R * n_chunks), gy);
+    *wpb_out = wpb;
+    *n_chunks_out = (int)n_chunks;
+    *chunk_out = chunk;
 }
 
-// SVGPFA_SPIKE_VARIANT (environment, experiments only) selects the kernel shape: NP*100 + UNROLL*10 + MINB.
+// SVGPFA_SPIKE_VARIANT (environment, experiments only): 1 = the register/global-load kernel (spike_fwd_bwd_kernel);
+// 12 = spike_tile_kernel with 2 pairs per lane, 111 = 1 pair per lane with a 128-register budget; default = 1 pair
+// per lane, 96 registers.  Measured on B200, config #5 shard of 2000 trials (ms): 1 -> 17.16, default -> 15.90,
+// 111 -> 15.80, 12 -> 16.43, 4 pairs per lane -> 18.4 (dropped).
 static int spike_variant() {
     static int v = -1;
     if (v < 0) {
@@ -348,31 +602,47 @@ static int spike_variant() {
     return v;
 }
 
+template <int NP, int MAXT, int MAXR>
+static void launch_tile(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st, int nsm,
+                        bool kgrad) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(spike_tile_kernel<true, NP, MAXT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+        cudaFuncSetAttribute(spike_tile_kernel<false, NP, MAXT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+        attr_set = true;
+    }
+    dim3 grid;
+    int wpb, n_chunks, chunk;
+    spike_grid(dims, nsm, NP, MAXT >= 256 ? 4 : (MAXT / 32 < 4 ? MAXT / 32 : 4), MAXT / 32, &grid, &wpb, &n_chunks, &chunk);
+    if (kgrad) spike_tile_kernel<true, NP, MAXT, MAXR><<<grid, 32 * wpb, ST_SMEM, st>>>(*dims, *buf, flags, n_chunks, chunk);
+    else spike_tile_kernel<false, NP, MAXT, MAXR><<<grid, 32 * wpb, ST_SMEM, st>>>(*dims, *buf, flags, n_chunks, chunk);
+}
+
 extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd", cudaSuccess);
     if (dims->R == 0 || dims->S == 0 || dims->N == 0) return SVGPFA_OK;
+    if (!dims->desc_host) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd: dims.desc_host", cudaSuccess);
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaStream_t st = (cudaStream_t)stream;
     const bool kgrad = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
-    const int var = spike_variant();
-#define SP_CASE(code, U, MB, NP)                                                     \
-    case code:                                                                       \
-        if (kgrad) launch_spike<true, U, MB, NP>(dims, buf, flags, st, nsm);         \
-        else launch_spike<false, U, MB, NP>(dims, buf, flags, st, nsm);              \
-        break;
-    switch (var) {          // measured on B200, config #5 shard of 2000 trials: 146 -> 17.1 ms, 126 -> 18.5, 148 -> 17.9,
-                            // 225 -> 17.0, 224 -> 17.8, 243 -> 17.5 (profiles/README.md); the default is 146
-        SP_CASE(126, 2, 6, 1)
-        SP_CASE(148, 4, 8, 1)
-        SP_CASE(225, 2, 5, 2)
-        SP_CASE(243, 4, 3, 2)
-        default:
-            if (kgrad) launch_spike<true, 4, 6, 1>(dims, buf, flags, st, nsm);
-            else launch_spike<false, 4, 6, 1>(dims, buf, flags, st, nsm);
+    int var = spike_variant();
+    if (var == 1) {     // measured on B200, config #5 shard of 2000 trials: 17.1 ms (profiles/README.md)
+        dim3 grid;
+        int wpb, n_chunks, chunk;
+        spike_grid(dims, nsm, 1, SP_WPB, SP_WPB, &grid, &wpb, &n_chunks, &chunk);
+        grid.y = ((dims->KM + 31) / 32 + SP_WPB - 1) / SP_WPB;
+        if (kgrad) spike_fwd_bwd_kernel<true, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
+        else spike_fwd_bwd_kernel<false, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
+    } else {
+        // NP = 2 needs every M_k even (the pairs of a lane share the latent)
+        bool even = true;
+        for (int k = 0; k < dims->K; ++k) even = even && (dims->desc_host[k].M % 2 == 0);
+        if (var == 12 && even) launch_tile<2, 160, 96>(dims, buf, flags, st, nsm, kgrad);
+        else if (var == 111) launch_tile<1, 128, 128>(dims, buf, flags, st, nsm, kgrad);
+        else launch_tile<1, 128, 96>(dims, buf, flags, st, nsm, kgrad);
     }
-#undef SP_CASE
     SVGPFA_CHECK_LAUNCH("spike_fwd_bwd");
     return SVGPFA_OK;
 }

@@ -45,6 +45,32 @@ def test_exp_neg_accuracy():
     assert err_ref.max() <= 4e-16
 
 
+def test_exp2m_accuracy():
+    """The spike kernel's pre-scaled exponential 2^(-w2/256) vs numpy (long double) over its whole range;
+    arguments above the limit are clamped (result ~6e-308 instead of 0 or a subnormal)."""
+    from svgpfa_b200 import _cabi
+    lib = _cabi.lib()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    w2 = torch.cat([torch.rand(200000, generator=gen, dtype=torch.float64) * 400.0,
+                    torch.rand(200000, generator=gen, dtype=torch.float64) * 2.0e4,
+                    torch.rand(100000, generator=gen, dtype=torch.float64) * 2.61e5,
+                    torch.rand(50000, generator=gen, dtype=torch.float64),
+                    torch.tensor([0.0, 0.5, 1.0, 127.5, 128.0, 255.999, 256.0, 2.609e5, 2.61e5, 3e6, 1e12, 1e300],
+                                 dtype=torch.float64)]).to(dev)
+    y = torch.empty_like(w2)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _cabi.check(lib.svgpfa_exp2m_eval(w2.data_ptr(), y.data_ptr(), w2.numel(), stream))
+    torch.cuda.synchronize()
+    w2, y = w2.cpu().numpy(), y.cpu().numpy()
+    inside = w2 <= 2.609e5
+    truth = np.exp2(-(w2[inside].astype(np.longdouble)) / np.longdouble(256)).astype(np.float64)
+    err = np.abs(y[inside] - truth) / truth
+    assert err.max() <= 4.5e-16, float(err.max())
+    assert y[w2 == 0.0][0] == 1.0
+    assert np.all(y[~inside] > 0.0) and np.all(y[~inside] < 1e-306)
+
+
 @pytest.mark.parametrize("name", ["tiny_mixed", "matlab_r5"])
 def test_stage_buffers_match_numpy_restatement(name):
     """Li, X, c, alpha, KL_rk, mu/var at quadrature points, abar (spike) against oracle/analytic_np.py."""
