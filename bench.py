@@ -345,17 +345,27 @@ def run_b200(args):
         e_stop.record()
         barrier()
         ms_e2e_p = e_start.elapsed_time(e_stop) / n_e2e
-        te = torch.tensor([ms_e2e, ms_e2e_p, float(h2d), float(d2h), float(h2d_p)], dtype=torch.float64, device=device)
+        # the same call without copy/compute overlap (one block, everything in order on one stream), for comparison
+        e_start.record()
+        for _ in range(2):
+            model.evalAndGradHost(io, copy_static=True, n_blocks=1)
+        e_stop.record()
+        barrier()
+        ms_e2e_serial = e_start.elapsed_time(e_stop) / 2
+        te = torch.tensor([ms_e2e, ms_e2e_p, float(h2d), float(d2h), float(h2d_p), ms_e2e_serial], dtype=torch.float64,
+                          device=device)
         if world > 1:
             mx = te.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = te.clone()
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            te = torch.stack([mx[0], mx[1], sm[2], sm[3], sm[4]])
+            te = torch.stack([mx[0], mx[1], sm[2], sm[3], sm[4], mx[5]])
         e2e = {"value": 1e3 / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(te[2]),
                "d2h_bytes_per_step": int(te[3]), "ms_per_step": float(te[0]), "wall_ms_per_step_rank0": wall_e2e,
                "params_only": {"value": 1e3 / float(te[1]), "h2d_bytes_per_step": int(te[4])},
-               "api": "svgpfa_elbo_grad_host (pinned host buffers; spikes, quadrature and parameters copied every step)"}
+               "unpipelined_ms_per_step": float(te[5]),
+               "api": "svgpfa_elbo_grad_host (pinned host buffers; spikes, quadrature and parameters copied every step; "
+                      "copies and kernels pipelined over blocks of trials on three streams)"}
         del io
 
     if rank != 0:

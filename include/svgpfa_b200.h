@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 1
+#define SVGPFA_ABI_VERSION 2
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -80,7 +80,12 @@ typedef struct svgpfa_dims {
     int64_t S;                    /* spikes in this shard */
     double  reg;                  /* prior-covariance regulariser (kernelsMatricesStore.py:113-116) */
     const svgpfa_latent_desc* desc_host;   /* HOST pointer, K rows */
+    int32_t r0, rn;               /* trial range [r0, r0 + rn) the per-trial stages work on; rn = 0: all R trials.
+                                     Sizes, strides and layouts are always those of the full shard (R); the host-buffer
+                                     entry uses the range to pipeline copies and kernels over blocks of trials. */
 } svgpfa_dims;
+
+#define SVGPFA_NTRIALS(d) ((d)->rn ? (d)->rn : (d)->R)
 
 #define SVGPFA_EMBED_TN 128
 
@@ -200,8 +205,9 @@ int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf
 int svgpfa_build_segments_host(int32_t R, int32_t N, const int64_t* counts_host,
                                int64_t* seg_off_host, int64_t* neuron_index_host);
 
-/* End-to-end entry with HOST buffers (pinned or pageable): copies parameters and spikes to the
- * device, runs svgpfa_elbo_grad and copies `shared`, gZ, gm, gcholvec, info back.  `dev` supplies the
+/* End-to-end entry with HOST buffers (pinned for overlap; pageable works): copies parameters and spikes to the
+ * device, runs the stages of svgpfa_elbo_grad and copies `shared`, gZ, gm, gcholvec, info back; all of it is
+ * ordered on `stream` from the caller's point of view (the call returns without synchronising).  `dev` supplies the
  * device-side buffers (same struct, device pointers); every *_host array mirrors the device one. */
 typedef struct svgpfa_host_io {
     const double* theta_host; const double* Z_host; const double* m_host; const double* cholvec_host;
@@ -209,6 +215,9 @@ typedef struct svgpfa_host_io {
     const double* spike_t_host; const int64_t* seg_off_host; const double* spike_cnt_host;
     double* shared_host; double* gZ_host; double* gm_host; double* gcholvec_host; int32_t* info_host;
     int32_t copy_static;      /* 1: also copy tq, wq, spikes, segments (first call); 0: parameters only */
+    int32_t n_blocks;         /* blocks of trials the copies and kernels are pipelined over (copy-in and copy-out
+                                 streams owned by the library run under the kernels of the neighbouring blocks);
+                                 0 = automatic (R / 2048, at most 16), 1 = everything in order on `stream` */
 } svgpfa_host_io;
 int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                           uint32_t flags, void* stream);

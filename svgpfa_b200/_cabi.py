@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -29,7 +29,7 @@ class LatentDesc(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("R", "N", "K", "Q", "KM", "MM", "PP", "TH", "Mmax", "n_ntiles")] + [
-        ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc))]
+        ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc)), ("r0", C.c_int32), ("rn", C.c_int32)]
 
 
 BUFFER_FIELDS = (
@@ -49,7 +49,7 @@ HOST_IO_FIELDS = ("theta_host", "Z_host", "m_host", "cholvec_host", "C_host", "d
 
 
 class HostIO(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in HOST_IO_FIELDS] + [("copy_static", C.c_int32)]
+    _fields_ = [(n, C.c_void_p) for n in HOST_IO_FIELDS] + [("copy_static", C.c_int32), ("n_blocks", C.c_int32)]
 
 
 # every symbol include/svgpfa_b200.h declares: name -> (restype, argtypes)

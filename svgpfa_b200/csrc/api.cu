@@ -322,13 +322,11 @@ extern "C" int svgpfa_finalize(const svgpfa_dims* dims, const svgpfa_buffers* bu
     return SVGPFA_OK;
 }
 
-extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
-    int rc = check_dims(dims, buf, "elbo_grad");
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t lat = SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
+namespace {
+
+// zero every accumulator of one evaluation (whole shard)
+void zero_accumulators(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool reuse_spike, cudaStream_t st) {
     const uint32_t kz = SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
-    const bool reuse_spike = (flags & SVGPFA_REUSE_SPIKE) && !(flags & (kz | SVGPFA_GRAD_EMBEDDING));
     cudaMemsetAsync(buf->shared, 0, sizeof(double) * shared_len(dims), st);
     cudaMemsetAsync(buf->term1_part, 0, sizeof(double) * SVGPFA_TERM1_SLOTS, st);
     cudaMemsetAsync(buf->info, 0, sizeof(int32_t) * 4, st);
@@ -337,24 +335,48 @@ extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* b
         cudaMemsetAsync(buf->dz_acc, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
         cudaMemsetAsync(buf->dth_part, 0, sizeof(double) * (size_t)dims->R * dims->TH, st);
     }
+}
+
+// the seven per-trial stages on the trial range of `dims` (r0, rn); stage events only when `mark`
+int run_trial_stages(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool reuse_spike,
+                     cudaStream_t st, bool mark) {
+    const uint32_t lat = SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
+    void* stream = (void*)st;
+    int rc;
     // (Running the quadrature chain on a high-priority side stream concurrently with the spike kernel was measured:
     //  32.41 vs 32.53 ms on the 2000-trial shard -- both kernels are limited by the same FP64 issue port and the spike
     //  kernel alone already holds every register of the SM, so the stages simply run one after the other.)
-    stage_mark(0, st);
+    if (mark) stage_mark(0, st);
     if (!(flags & SVGPFA_REUSE_KZZ)) { rc = svgpfa_kzz_chol_fwd(dims, buf, stream); if (rc) return rc; }
-    stage_mark(1 + SVGPFA_STAGE_KZZ_CHOL, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_KZZ_CHOL, st);
     rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc;
-    stage_mark(1 + SVGPFA_STAGE_INDPOINTS_FWD, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_INDPOINTS_FWD, st);
     rc = svgpfa_quad_latent_fwd(dims, buf, stream); if (rc) return rc;
-    stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_FWD, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_FWD, st);
     rc = svgpfa_quad_embed_fwd_bwd(dims, buf, flags, stream); if (rc) return rc;
-    stage_mark(1 + SVGPFA_STAGE_QUAD_EMBED, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_EMBED, st);
     if (flags & lat) { rc = svgpfa_quad_latent_bwd(dims, buf, flags, stream); if (rc) return rc; }
-    stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_BWD, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_BWD, st);
     if (!reuse_spike) { rc = svgpfa_spike_fwd_bwd(dims, buf, flags, stream); if (rc) return rc; }
-    stage_mark(1 + SVGPFA_STAGE_SPIKE, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_SPIKE, st);
     if (flags & lat) { rc = svgpfa_indpoints_bwd(dims, buf, flags, stream); if (rc) return rc; }
-    stage_mark(1 + SVGPFA_STAGE_INDPOINTS_BWD, st);
+    if (mark) stage_mark(1 + SVGPFA_STAGE_INDPOINTS_BWD, st);
+    return SVGPFA_OK;
+}
+
+}  // namespace
+
+extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
+    int rc = check_dims(dims, buf, "elbo_grad");
+    if (rc) return rc;
+    if (dims->r0 != 0 || (dims->rn != 0 && dims->rn != dims->R))
+        return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad: a trial range is only valid on the per-stage entry points", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t kz = SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
+    const bool reuse_spike = (flags & SVGPFA_REUSE_SPIKE) && !(flags & (kz | SVGPFA_GRAD_EMBEDDING));
+    zero_accumulators(dims, buf, flags, reuse_spike, st);
+    rc = run_trial_stages(dims, buf, flags, reuse_spike, st, true);
+    if (rc) return rc;
     rc = svgpfa_finalize(dims, buf, flags, stream);
     stage_mark(1 + SVGPFA_STAGE_FINALIZE, st);
     return rc;
@@ -396,49 +418,139 @@ extern "C" int svgpfa_build_segments_host(int32_t R, int32_t N, const int64_t* c
     return SVGPFA_OK;
 }
 
+namespace {
+
+// Side streams and events of the pipelined host-buffer entry, one set per (host thread, device), created on first use.
+constexpr int HP_MAX_BLOCKS = 16;
+struct HostPipe {
+    bool init = false;
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t start = nullptr, drained = nullptr, copied[HP_MAX_BLOCKS], done[HP_MAX_BLOCKS];
+};
+thread_local HostPipe g_pipes[16];
+
+HostPipe* host_pipe() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return nullptr;
+    HostPipe& p = g_pipes[dev];
+    if (!p.init) {
+        if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&p.drained, cudaEventDisableTiming);
+        for (int i = 0; i < HP_MAX_BLOCKS; ++i) {
+            cudaEventCreateWithFlags(&p.copied[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming);
+        }
+        p.init = true;
+    }
+    return &p;
+}
+
+}  // namespace
+
 extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                                      uint32_t flags, void* stream) {
     int rc = check_dims(dims, dev, "elbo_grad_host");
     if (rc) return rc;
     if (!io) return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host", cudaSuccess);
+    if (!dims->desc_host) return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host: dims.desc_host", cudaSuccess);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = dims->R, D = sizeof(double);
-#define H2D(dst, src, bytes)                                                                          \
+    const uint32_t flags_run = flags & ~(uint32_t)(SVGPFA_REUSE_KZZ | SVGPFA_REUSE_SPIKE);   // every input is new
+#define CPY(dst, src, bytes, kind, s_)                                                                \
     do {                                                                                              \
-        if ((bytes) > 0) {                                                                            \
-            cudaError_t e = cudaMemcpyAsync((void*)(dst), (src), (bytes), cudaMemcpyHostToDevice, st); \
-            if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host H2D", e);     \
+        if ((bytes) > 0 && (dst) && (src)) {                                                          \
+            cudaError_t e = cudaMemcpyAsync((void*)(dst), (src), (bytes), kind, s_);                  \
+            if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host copy", e);   \
         }                                                                                             \
     } while (0)
-#define D2H(dst, src, bytes)                                                                          \
-    do {                                                                                              \
-        if ((bytes) > 0 && (dst)) {                                                                   \
-            cudaError_t e = cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, st);        \
-            if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host D2H", e);     \
-        }                                                                                             \
-    } while (0)
-    if (io->copy_static) {
-        H2D(dev->tq, io->tq_host, R * dims->Q * D);
-        H2D(dev->wq, io->wq_host, R * dims->Q * D);
-        H2D(dev->spike_t, io->spike_t_host, (size_t)dims->S * D);
-        H2D(dev->seg_off, io->seg_off_host, (R * dims->N + 1) * sizeof(int64_t));
-        H2D(dev->spike_cnt, io->spike_cnt_host, (size_t)dims->N * D);
+#define H2D(dst, src, bytes, s_) CPY(dst, src, bytes, cudaMemcpyHostToDevice, s_)
+#define D2H(dst, src, bytes, s_) CPY(dst, src, bytes, cudaMemcpyDeviceToHost, s_)
+    // blocks of trials: copies of block b+1 (copy-in stream) and of block b-1's gradients (copy-out stream) run
+    // under the kernels of block b (caller's stream); 1 block = everything in order on the caller's stream
+    int nb = io->n_blocks;
+    if (nb <= 0) nb = (int)(R / 2048);
+    if (nb > HP_MAX_BLOCKS) nb = HP_MAX_BLOCKS;
+    if (nb > (int)R) nb = (int)R;
+    if (nb < 1) nb = 1;
+    if (io->copy_static && (!io->seg_off_host || !io->spike_t_host))
+        return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host: copy_static needs seg_off_host and spike_t_host", cudaSuccess);
+    HostPipe* hp = nb > 1 ? host_pipe() : nullptr;
+    if (!hp) nb = 1;
+    cudaStream_t s_in = hp ? hp->in : st, s_out = hp ? hp->out : st;
+    H2D(dev->theta, io->theta_host, (size_t)dims->TH * D, st);
+    H2D(dev->C, io->C_host, (size_t)dims->N * dims->K * D, st);
+    H2D(dev->d, io->d_host, (size_t)dims->N * D, st);
+    if (io->copy_static) H2D(dev->spike_cnt, io->spike_cnt_host, (size_t)dims->N * D, st);
+    zero_accumulators(dims, dev, flags_run, false, st);
+    if (hp) {
+        cudaEventRecord(hp->start, st);            // earlier work on the caller's stream may still read the buffers
+        cudaStreamWaitEvent(s_in, hp->start, 0);
     }
-    H2D(dev->theta, io->theta_host, (size_t)dims->TH * D);
-    H2D(dev->Z, io->Z_host, R * dims->KM * D);
-    H2D(dev->m, io->m_host, R * dims->KM * D);
-    H2D(dev->cholvec, io->cholvec_host, R * dims->PP * D);
-    H2D(dev->C, io->C_host, (size_t)dims->N * dims->K * D);
-    H2D(dev->d, io->d_host, (size_t)dims->N * D);
-    rc = svgpfa_elbo_grad(dims, dev, flags, stream);
+    auto r_of = [&](int b) { return (size_t)(R * (size_t)b / (size_t)nb); };
+    for (int b = 0; b < nb; ++b) {
+        const size_t r0 = r_of(b), r1 = r_of(b + 1), n = r1 - r0;
+        for (int k = 0; k < dims->K; ++k) {
+            const svgpfa_latent_desc& ds = dims->desc_host[k];
+            const size_t om = R * ds.moff + r0 * ds.M, op = R * ds.poff + r0 * ds.P;
+            H2D(dev->Z + om, io->Z_host + om, n * ds.M * D, s_in);
+            H2D(dev->m + om, io->m_host + om, n * ds.M * D, s_in);
+            H2D(dev->cholvec + op, io->cholvec_host + op, n * ds.P * D, s_in);
+        }
+        if (io->copy_static) {
+            H2D(dev->tq + r0 * dims->Q, io->tq_host + r0 * dims->Q, n * dims->Q * D, s_in);
+            H2D(dev->wq + r0 * dims->Q, io->wq_host + r0 * dims->Q, n * dims->Q * D, s_in);
+            const size_t g0 = r0 * dims->N, g1 = r1 * dims->N;
+            H2D(dev->seg_off + g0, io->seg_off_host + g0, (g1 - g0 + 1) * sizeof(int64_t), s_in);
+            const int64_t s0 = io->seg_off_host[g0], s1 = io->seg_off_host[g1];
+            H2D(dev->spike_t + s0, io->spike_t_host + s0, (size_t)(s1 - s0) * D, s_in);
+        }
+        if (hp) cudaEventRecord(hp->copied[b], s_in);
+    }
+    for (int b = 0; b < nb; ++b) {
+        const size_t r0 = r_of(b), r1 = r_of(b + 1), n = r1 - r0;
+        svgpfa_dims db = *dims;
+        db.r0 = (int32_t)r0;
+        db.rn = nb > 1 ? (int32_t)n : 0;
+        if (hp) cudaStreamWaitEvent(st, hp->copied[b], 0);
+        if (n > 0) {
+            rc = run_trial_stages(&db, dev, flags_run, false, st, nb == 1);
+            if (rc) return rc;
+        }
+        if (hp) {
+            cudaEventRecord(hp->done[b], st);
+            cudaStreamWaitEvent(s_out, hp->done[b], 0);
+        }
+        if (nb > 1) {                              // this block's per-trial gradients
+            for (int k = 0; k < dims->K; ++k) {
+                const svgpfa_latent_desc& ds = dims->desc_host[k];
+                const size_t om = R * ds.moff + r0 * ds.M, op = R * ds.poff + r0 * ds.P;
+                if (flags & SVGPFA_GRAD_INDLOCS) D2H(io->gZ_host ? io->gZ_host + om : nullptr, dev->gZ + om, n * ds.M * D, s_out);
+                if (flags & SVGPFA_GRAD_POSTERIOR) {
+                    D2H(io->gm_host ? io->gm_host + om : nullptr, dev->gm + om, n * ds.M * D, s_out);
+                    D2H(io->gcholvec_host ? io->gcholvec_host + op : nullptr, dev->gcholvec + op, n * ds.P * D, s_out);
+                }
+            }
+        }
+    }
+    rc = svgpfa_finalize(dims, dev, flags_run, stream);
+    if (nb == 1) stage_mark(1 + SVGPFA_STAGE_FINALIZE, st);
     if (rc) return rc;
-    D2H(io->shared_host, dev->shared, shared_len(dims) * D);
-    if (flags & SVGPFA_GRAD_INDLOCS) D2H(io->gZ_host, dev->gZ, R * dims->KM * D);
-    if (flags & SVGPFA_GRAD_POSTERIOR) {
-        D2H(io->gm_host, dev->gm, R * dims->KM * D);
-        D2H(io->gcholvec_host, dev->gcholvec, R * dims->PP * D);
+    D2H(io->shared_host, dev->shared, shared_len(dims) * D, st);
+    D2H(io->info_host, dev->info, 4 * sizeof(int32_t), st);
+    if (nb == 1) {
+        if (flags & SVGPFA_GRAD_INDLOCS) D2H(io->gZ_host, dev->gZ, R * dims->KM * D, st);
+        if (flags & SVGPFA_GRAD_POSTERIOR) {
+            D2H(io->gm_host, dev->gm, R * dims->KM * D, st);
+            D2H(io->gcholvec_host, dev->gcholvec, R * dims->PP * D, st);
+        }
+    } else {
+        cudaEventRecord(hp->drained, s_out);       // the caller's stream drains only after the last gradient copy
+        cudaStreamWaitEvent(st, hp->drained, 0);
     }
-    D2H(io->info_host, dev->info, 4 * sizeof(int32_t));
+#undef CPY
 #undef H2D
 #undef D2H
     return SVGPFA_OK;

@@ -309,6 +309,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+inline int svgpfa_ntrials(const svgpfa_dims* d) { return SVGPFA_NTRIALS(d); }
+
 // host-side error plumbing (api.cu)
 int svgpfa_set_error(int code, const char* where, cudaError_t ce);
 #define SVGPFA_CHECK_LAUNCH(where)                                          \

@@ -19,7 +19,7 @@ template <bool ONEWARP>
 __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
     auto sync = [] { if (ONEWARP) __syncwarp(); else __syncthreads(); };
     extern __shared__ double sm[];
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const int M = ds.M, ld = ld_of(M);
     double* A = sm;                 // M x ld : Kzz -> L
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
 __global__ void __launch_bounds__(IP_THREADS) indpoints_fwd_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
     extern __shared__ double sm[];
     __shared__ double red[32];
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const int M = ds.M, ld = ld_of(M);
     double* A = sm;                 // Li
@@ -163,7 +163,7 @@ __device__ __forceinline__ void mm_mma(int MP, bool lower_only, FA a, FB b, FR r
 __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     extern __shared__ double sm[];
     __shared__ double red[32];
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const int M = ds.M, MP = round_up(M, 8), ld = MP + 4, MS = MP * ld;       // ld = 4 mod 8: conflict-free fragments
     const bool need_post = flags & SVGPFA_GRAD_POSTERIOR;
@@ -334,10 +334,10 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
     const size_t smem = ip_smem(dims->Mmax, 2, 2);
     if (dims->Mmax <= 32) {
         cudaFuncSetAttribute(kzz_chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kzz_chol_kernel<true><<<dim3(dims->R, dims->K), 32, smem, (cudaStream_t)stream>>>(*dims, *buf);
+        kzz_chol_kernel<true><<<dim3(svgpfa_ntrials(dims), dims->K), 32, smem, (cudaStream_t)stream>>>(*dims, *buf);
     } else {
         cudaFuncSetAttribute(kzz_chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kzz_chol_kernel<false><<<dim3(dims->R, dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
+        kzz_chol_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
     }
     SVGPFA_CHECK_LAUNCH("kzz_chol_fwd");
     return SVGPFA_OK;
@@ -348,7 +348,7 @@ extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffer
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 2, 2);
     cudaFuncSetAttribute(indpoints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    indpoints_fwd_kernel<<<dim3(dims->R, dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    indpoints_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     SVGPFA_CHECK_LAUNCH("indpoints_fwd");
     return SVGPFA_OK;
 }
@@ -359,7 +359,7 @@ extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     const size_t smem = ip_smem(dims->Mmax, 6, 6);
     cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    indpoints_bwd_kernel<<<dim3(dims->R, dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;
 }

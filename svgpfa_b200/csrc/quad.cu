@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(QL_THREADS) quad_latent_fwd_kernel(svgpfa_dims
     extern __shared__ __align__(16) double sm[];
     __shared__ double etab[64];
     svgpfa_load_exp_tab64(etab);
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const QLGeom g = ql_geom(ds.M);
     const QLSmem s = ql_carve(sm, g, false);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(QL_THREADS, BIG ? 1 : 4) quad_latent_bwd_kerne
     __shared__ double red[32];
     __shared__ double etab[64];
     svgpfa_load_exp_tab64(etab);
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const QLGeom g = ql_geom(ds.M);
     const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
@@ -470,11 +470,11 @@ __global__ void __launch_bounds__(EM_THREADS, 3) quad_embed_kernel(svgpfa_dims d
     if (tid < EM_TN) dvec[tid] = (n0 + tid < N) ? bf.d[n0 + tid] : 0.0;
     double t1 = 0.0, dd_acc = 0.0;
     const int qtiles = (Q + EM_TQ - 1) / EM_TQ;
-    const int nitems = dm.R * qtiles;
+    const int nitems = (dm.rn ? dm.rn : dm.R) * qtiles;
     const size_t part_off = (size_t)tile * dm.R * Q * K;
     __syncthreads();
     for (int it = blockIdx.y; it < nitems; it += gridDim.y) {
-        const int r = it / qtiles, q0 = (it - r * qtiles) * EM_TQ;
+        const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EM_TQ;
         // stage mu, var (transposed) and weights of the 16 points
         for (int idx = tid; idx < EM_TQ * K; idx += EM_THREADS) {
             const int qq = idx / K, kk = idx - qq * K;
@@ -588,7 +588,7 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, false);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    quad_latent_fwd_kernel<<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    quad_latent_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     SVGPFA_CHECK_LAUNCH("quad_latent_fwd");
     return SVGPFA_OK;
 }
@@ -604,11 +604,11 @@ extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buff
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_latent_bwd: shared memory", cudaSuccess);
     if (dims->Mmax > 44) {
         cudaFuncSetAttribute(quad_latent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        quad_latent_bwd_kernel<true><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+        quad_latent_bwd_kernel<true><<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     } else {
         cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        quad_latent_bwd_kernel<false><<<dim3(dims->R, dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+        quad_latent_bwd_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     }
     SVGPFA_CHECK_LAUNCH("quad_latent_bwd");
     return SVGPFA_OK;
@@ -627,7 +627,7 @@ extern "C" int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_b
     cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int ntiles = (dims->N + EM_TN - 1) / EM_TN;
     const int qtiles = (dims->Q + EM_TQ - 1) / EM_TQ;
-    const long nitems = (long)dims->R * qtiles;
+    const long nitems = (long)svgpfa_ntrials(dims) * qtiles;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     __shared__ double red[32];
     __shared__ double etab[64];
     svgpfa_load_exp_tab64(etab);
-    const int r = blockIdx.x, k = blockIdx.y;
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
     const int M = ds.M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -373,7 +373,7 @@ void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flag
     cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    quad_latent_mma_kernel<MT, BWD><<<dim3(dims->R, dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
+    quad_latent_mma_kernel<MT, BWD><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
 }
 
 // ======================================================================================
@@ -428,11 +428,11 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
         for (int b = 0; b < KT; ++b) cm[a][b][0] = cm[a][b][1] = cv[a][b][0] = cv[a][b][1] = 0.0;
     double t1 = 0.0;
     const int qtiles = (Q + EMM_TQ - 1) / EMM_TQ;
-    const int nitems = dm.R * qtiles;
+    const int nitems = (dm.rn ? dm.rn : dm.R) * qtiles;
     const size_t part_off = (size_t)tile * dm.R * K * Q;
     __syncthreads();
     for (int it = blockIdx.y; it < nitems; it += gridDim.y) {
-        const int r = it / qtiles, q0 = (it - r * qtiles) * EMM_TQ;
+        const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EMM_TQ;
         for (int idx = tid; idx < EMM_TQ * KP; idx += EMM_THREADS) {
             const int qq = idx / KP, kk = idx - qq * KP;
             const bool v = (q0 + qq) < Q && kk < K;
@@ -562,7 +562,7 @@ void launch_emm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t fla
     cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int ntiles = (dims->N + EMM_TN - 1) / EMM_TN;
     const int qtiles = (dims->Q + EMM_TQ - 1) / EMM_TQ;
-    const long nitems = (long)dims->R * qtiles;
+    const long nitems = (long)svgpfa_ntrials(dims) * qtiles;
     int dev = 0, nsm = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

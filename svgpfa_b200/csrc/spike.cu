@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa
     svgpfa_load_exp_tab(etab);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x / n_chunks, nc = blockIdx.x - r * n_chunks;
+    const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
     const int grp = blockIdx.y * SP_WPB + warp;
     if (grp * 32 * NP >= dm.KM) return;                  // whole warp out of range
     PairInfo pi[NP];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgp
     svgpfa_load_exp2m_tab(st_smem);
     const unsigned etab = svgpfa_exp2m_lane_tab(st_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int r = blockIdx.x / n_chunks, nc = blockIdx.x - r * n_chunks;
+    const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
     const int grp = blockIdx.y * wpb + warp;
     // a warp past the last pair still takes part in the staging and the barriers; its lanes are inactive
     const PairInfo pi = pair_info(dm, bf, (grp * 32 + lane) * NP, lane);       // first pair of the lane
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm,
     double* as = zs + dm.KM;         // KM   scale^2 alpha
     double* knh = as + dm.KM;        // K    kernel constants, computed once per CTA
     double* kip = knh + dm.K;        // K    1/p (0 for the exponential-quadratic kernel)
-    const int r = blockIdx.x / n_split, part = blockIdx.x - r * n_split;
+    const int rl = blockIdx.x / n_split, r = dm.r0 + rl, part = blockIdx.x - rl * n_split;
     for (int k = 0; k < dm.K; ++k) {
         const svgpfa_latent_desc ds = bf.desc[k];
         const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
@@ -531,11 +531,11 @@ __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm
     __shared__ double red[32];
     const int lane = threadIdx.x & 31;
     const int wpb = SG_THREADS / 32;
-    const int64_t nseg = (int64_t)dm.R * dm.N;
+    const int64_t seg0 = (int64_t)dm.r0 * dm.N, nseg = seg0 + (int64_t)(dm.rn ? dm.rn : dm.R) * dm.N;
     const int K = dm.K;
     double* gC = bf.shared + SVGPFA_SHARED_HDR;
     double val = 0.0;
-    for (int64_t sg = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); sg < nseg; sg += (int64_t)gridDim.x * wpb) {
+    for (int64_t sg = seg0 + (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); sg < nseg; sg += (int64_t)gridDim.x * wpb) {
         const int64_t s0 = bf.seg_off[sg], s1 = bf.seg_off[sg + 1];
         if (s0 == s1) continue;
         const int n = (int)(sg % dm.N);
@@ -578,12 +578,13 @@ static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, in
     }
     const int gy = (LG + wpb - 1) / wpb;
     const long target_warps = (long)nsm * 64 * 4 / np;
-    long n_chunks = (target_warps + (long)dims->R * LG - 1) / ((long)dims->R * LG);
+    const long Rn = svgpfa_ntrials(dims);
+    long n_chunks = (target_warps + Rn * LG - 1) / (Rn * LG);
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > dims->N) n_chunks = dims->N;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
-    *grid = dim3((unsigned)(dims->R * n_chunks), gy);
+    *grid = dim3((unsigned)(Rn * n_chunks), gy);
     *wpb_out = wpb;
     *n_chunks_out = (int)n_chunks;
     *chunk_out = chunk;
@@ -653,10 +654,11 @@ extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_b
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    int n_split = (nsm * 8 + dims->R - 1) / dims->R;
+    const int Rn = svgpfa_ntrials(dims);
+    int n_split = (nsm * 8 + Rn - 1) / Rn;
     if (n_split < 1) n_split = 1;
     const size_t smem = sizeof(double) * (2 * (size_t)dims->KM + 2 * (size_t)dims->K);
-    spike_means_kernel<<<dims->R * n_split, SM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, n_split);
+    spike_means_kernel<<<Rn * n_split, SM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, n_split);
     SVGPFA_CHECK_LAUNCH("spike_latent_means");
     return SVGPFA_OK;
 }
@@ -666,7 +668,7 @@ int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* bu
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const long nseg = (long)dims->R * dims->N;
+    const long nseg = (long)svgpfa_ntrials(dims) * dims->N;
     long blocks = (nseg + SG_THREADS / 32 - 1) / (SG_THREADS / 32);
     if (blocks > (long)nsm * 16) blocks = (long)nsm * 16;
     spike_gather_kernel<<<(unsigned)blocks, SG_THREADS, 0, stream>>>(*dims, *buf);

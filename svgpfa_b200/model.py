@@ -406,7 +406,7 @@ class B200SVLowerBound:
                     shared=z(self._shared_len), gZ=z(R * self._KM), gm=z(R * self._KM), gcholvec=z(R * self._PP),
                     info=z(4, torch.int32))
 
-    def evalAndGradHost(self, io, flags=_cabi.GRAD_ALL, copy_static=True):
+    def evalAndGradHost(self, io, flags=_cabi.GRAD_ALL, copy_static=True, n_blocks=0):
         """One unit of work through the C ABI with HOST buffers: host->device copies of the inputs,
         ``svgpfa_elbo_grad``, device->host copies of the bound and the gradients, all on the current
         stream; returns after the stream has drained.  Returns (elbo, h2d_bytes, d2h_bytes)."""
@@ -424,6 +424,7 @@ class B200SVLowerBound:
                      "shared", "gZ", "gm", "gcholvec", "info"):
             setattr(hio, name + "_host", io[name].data_ptr())
         hio.copy_static = 1 if copy_static else 0
+        hio.n_blocks = int(n_blocks)          # 0: automatic; 1: no copy/compute overlap
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().svgpfa_elbo_grad_host(ctypes.byref(self._dims), ctypes.byref(b), ctypes.byref(hio),
                                                           flags, self._stream()), "elbo_grad_host")
