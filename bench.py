@@ -388,7 +388,7 @@ def run_b200(args):
     # secondary: SURVEY.md 8d cost model (10 M flops per spike-latent + one exp at the libdevice exp's measured cost)
     c_exp_libdevice = 2.0 * peaks["dfma"] / peaks["exp"]
     survey_flops = cnt["F_spike"] + cnt["N_exp_spike"] * c_exp_libdevice + cnt["N_sin_spike"] * 2.0 * c_sin
-    roofline = {"bound": "fp64", "kernel": "spike_fwd_bwd_kernel", "achieved": achieved, "peak": peak_tf,
+    roofline = {"bound": "fp64", "kernel": "spike_tile_kernel", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                 "peak_source": "DFMA throughput measured in this run (svgpfa_peak_probe); MEASURED_PEAKS.json has "
                                "no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
@@ -403,6 +403,23 @@ def run_b200(args):
     total_equiv = (cnt["F_setup"] + cnt["F_quad"] + cnt["F_embed"] + 2.0 * slots
                    + cnt["N_exp_other"] * 2.0 * 7.0)
     roofline["whole_step_frac"] = total_equiv / (ms_step * 1e-3) / 1e12 / peak_tf
+    # every other stage against the same FP64 peak with SURVEY.md 8d's flop counts (an exp counted at 2 x 13 flops, the
+    # library's instruction count): how far each fused kernel is from the FP64 roof, not only the dominant one
+    stage = {n: float(v) * 1e-3 for n, v in zip(_cabi.STAGES, st)}
+    Rl, K_, M_, Q_, N_ = r1 - r0, cfg["K"], cfg["M"], cfg["Q"], cfg["N"]
+    exp_fl = 26.0
+
+    def frac_of(flops, seconds):
+        return None if seconds <= 0 else flops / seconds / 1e12 / peak_tf
+    roofline["other_stages"] = {
+        "model": "SURVEY.md 8d flop counts (split between forward and backward as 1:2) + 26 flop-equivalents per "
+                 "kernel evaluation / exp, over the stage's CUDA-event time, as a fraction of the same measured DFMA peak",
+        "kzz_chol+indpoints_fwd+indpoints_bwd": frac_of(cnt["F_setup"] + exp_fl * Rl * K_ * M_ * (M_ + 1),
+                                                        stage["kzz_chol"] + stage["indpoints_fwd"] + stage["indpoints_bwd"]),
+        "quad_latent_fwd": frac_of(cnt["F_quad"] / 3.0 + exp_fl * Rl * K_ * Q_ * M_, stage["quad_latent_fwd"]),
+        "quad_latent_bwd": frac_of(cnt["F_quad"] * 2.0 / 3.0 + exp_fl * 2.0 * Rl * K_ * Q_ * M_, stage["quad_latent_bwd"]),
+        "quad_embed": frac_of(cnt["F_embed"] + exp_fl * Rl * Q_ * N_, stage["quad_embed"]),
+    }
     try:        # DRAM traffic of the launch from the committed ncu --set full capture of the same configuration
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_spike_traffic.json"))).get(args.config)
         if tr and tr["trials"] == r1 - r0:

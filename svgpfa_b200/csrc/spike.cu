@@ -481,20 +481,24 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgp
 constexpr int SM_THREADS = 256;
 
 __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm, svgpfa_buffers bf, int n_split) {
-    extern __shared__ double sm[];
-    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
-    svgpfa_load_exp_tab(etab);
-    double* zs = sm;                 // KM
-    double* as = zs + dm.KM;         // KM   scale^2 alpha
-    double* knh = as + dm.KM;        // K    kernel constants, computed once per CTA
-    double* kip = knh + dm.K;        // K    1/p (0 for the exponential-quadratic kernel)
+    extern __shared__ __align__(16) double sm[];
+    double* etab = sm;                                   // replicated exp table (svgpfa_exp2m)
+    double* zs = etab + SVGPFA_EXP2M_TAB_BYTES / 8;      // KM   z_j sc_k (pre-scaled; periodic: z_j)
+    double* as = zs + dm.KM;                             // KM   scale^2 alpha
+    double* ksc = as + dm.KM;                            // K    sc_k
+    double* kip = ksc + dm.K;                            // K    1/p (0 for the exponential-quadratic kernel)
+    svgpfa_load_exp2m_tab(etab);
+    const unsigned lane_tab = svgpfa_exp2m_lane_tab(etab);
     const int rl = blockIdx.x / n_split, r = dm.r0 + rl, part = blockIdx.x - rl * n_split;
     for (int k = 0; k < dm.K; ++k) {
         const svgpfa_latent_desc ds = bf.desc[k];
         const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-        if (threadIdx.x == 0) { knh[k] = kc.nh; kip[k] = kc.type == SVGPFA_KERNEL_PERIODIC ? kc.invp : 0.0; }
+        const double sc = sqrt(-kc.nh * SVGPFA_EXP2M_INV_L);
+        const bool per = kc.type == SVGPFA_KERNEL_PERIODIC;
+        if (threadIdx.x == 0) { ksc[k] = sc; kip[k] = per ? kc.invp : 0.0; }
         for (int j = threadIdx.x; j < ds.M; j += blockDim.x) {
-            zs[ds.moff + j] = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + j];
+            const double z = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + j];
+            zs[ds.moff + j] = per ? z : z * sc;
             as[ds.moff + j] = kc.s2 * bf.alpha[(size_t)r * dm.KM + ds.moff + j];
         }
     }
@@ -504,18 +508,20 @@ __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm,
         const double t = bf.spike_t[s];
         for (int k = 0; k < dm.K; ++k) {
             const int M = bf.desc[k].M, off = bf.desc[k].moff;
-            const double nh = knh[k], ip = kip[k];
+            const double sc = ksc[k], ip = kip[k];
             double mu = 0.0;
             if (ip == 0.0) {
+                const double tsc = t * sc;
 #pragma unroll 4
                 for (int j = 0; j < M; ++j) {
-                    const double dl = t - zs[off + j];
-                    mu = fma(svgpfa_exp_neg(nh * (dl * dl), etab), as[off + j], mu);
+                    const double w = tsc - zs[off + j];
+                    mu = fma(svgpfa_exp2m(svgpfa_exp2m_clamp(w * w), lane_tab), as[off + j], mu);
                 }
             } else {
+#pragma unroll 2
                 for (int j = 0; j < M; ++j) {
-                    const double sn = sinpi((t - zs[off + j]) * ip);
-                    mu = fma(svgpfa_exp_neg(nh * (sn * sn), etab), as[off + j], mu);
+                    const double w = sinpi((t - zs[off + j]) * ip) * sc;
+                    mu = fma(svgpfa_exp2m(svgpfa_exp2m_clamp(w * w), lane_tab), as[off + j], mu);
                 }
             }
             bf.mu_s[(size_t)s * dm.K + k] = mu;
@@ -657,7 +663,8 @@ extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_b
     const int Rn = svgpfa_ntrials(dims);
     int n_split = (nsm * 8 + Rn - 1) / Rn;
     if (n_split < 1) n_split = 1;
-    const size_t smem = sizeof(double) * (2 * (size_t)dims->KM + 2 * (size_t)dims->K);
+    const size_t smem = SVGPFA_EXP2M_TAB_BYTES + sizeof(double) * (2 * (size_t)dims->KM + 2 * (size_t)dims->K);
+    cudaFuncSetAttribute(spike_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     spike_means_kernel<<<Rn * n_split, SM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, n_split);
     SVGPFA_CHECK_LAUNCH("spike_latent_means");
     return SVGPFA_OK;
