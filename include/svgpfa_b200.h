@@ -217,7 +217,7 @@ typedef struct svgpfa_host_io {
     int32_t copy_static;      /* 1: also copy tq, wq, spikes, segments (first call); 0: parameters only */
     int32_t n_blocks;         /* blocks of trials the copies and kernels are pipelined over (copy-in and copy-out
                                  streams owned by the library run under the kernels of the neighbouring blocks);
-                                 0 = automatic (R / 2048, at most 16), 1 = everything in order on `stream` */
+                                 0 = automatic (R / 312, at most 16), 1 = everything in order on `stream` */
 } svgpfa_host_io;
 int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                           uint32_t flags, void* stream);

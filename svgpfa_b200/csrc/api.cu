@@ -471,7 +471,9 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
     // blocks of trials: copies of block b+1 (copy-in stream) and of block b-1's gradients (copy-out stream) run
     // under the kernels of block b (caller's stream); 1 block = everything in order on the caller's stream
     int nb = io->n_blocks;
-    if (nb <= 0) nb = (int)(R / 2048);
+    if (nb <= 0) nb = (int)(R / 312);           // measured (tools/bench_host.py): 2500 trials 50.4 / 41.8 / 41.0 ms with
+                                                // 1 / 4 / 8 blocks; 20000 trials 324.6 / 314.1 / 308.7 ms with 4 / 8 / 16
+                                                // (32 blocks: 336 ms -- launch and copy calls start to dominate)
     if (nb > HP_MAX_BLOCKS) nb = HP_MAX_BLOCKS;
     if (nb > (int)R) nb = (int)R;
     if (nb < 1) nb = 1;
@@ -490,15 +492,35 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
         cudaStreamWaitEvent(s_in, hp->start, 0);
     }
     auto r_of = [&](int b) { return (size_t)(R * (size_t)b / (size_t)nb); };
-    for (int b = 0; b < nb; ++b) {
-        const size_t r0 = r_of(b), r1 = r_of(b + 1), n = r1 - r0;
+    // K-major arrays: the block's trials are K separate runs, one per latent; with a uniform M they form a 2-D copy
+    bool uniform = true;
+    for (int k = 1; k < dims->K; ++k) uniform = uniform && dims->desc_host[k].M == dims->desc_host[0].M;
+    auto kmajor = [&](void* d, const void* h, bool per_p, size_t r0, size_t n, cudaMemcpyKind kind, cudaStream_t s_) -> cudaError_t {
+        if (!d || !h || n == 0) return cudaSuccess;
+        char* dc = (char*)d;
+        const char* hc = (const char*)h;
+        if (uniform) {
+            const size_t w = per_p ? dims->desc_host[0].P : dims->desc_host[0].M;
+            return cudaMemcpy2DAsync(dc + r0 * w * D, R * w * D, hc + r0 * w * D, R * w * D, n * w * D, dims->K, kind, s_);
+        }
         for (int k = 0; k < dims->K; ++k) {
             const svgpfa_latent_desc& ds = dims->desc_host[k];
-            const size_t om = R * ds.moff + r0 * ds.M, op = R * ds.poff + r0 * ds.P;
-            H2D(dev->Z + om, io->Z_host + om, n * ds.M * D, s_in);
-            H2D(dev->m + om, io->m_host + om, n * ds.M * D, s_in);
-            H2D(dev->cholvec + op, io->cholvec_host + op, n * ds.P * D, s_in);
+            const size_t w = per_p ? ds.P : ds.M, o = (R * (per_p ? ds.poff : ds.moff) + r0 * w) * D;
+            cudaError_t e = cudaMemcpyAsync(dc + o, hc + o, n * w * D, kind, s_);
+            if (e != cudaSuccess) return e;
         }
+        return cudaSuccess;
+    };
+#define KM(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e = (call);                                                                       \
+        if (e != cudaSuccess) return svgpfa_set_error(SVGPFA_E_CUDA, "elbo_grad_host block copy", e); \
+    } while (0)
+    auto copy_in = [&](int b) -> int {
+        const size_t r0 = r_of(b), r1 = r_of(b + 1), n = r1 - r0;
+        KM(kmajor((void*)dev->Z, io->Z_host, false, r0, n, cudaMemcpyHostToDevice, s_in));
+        KM(kmajor((void*)dev->m, io->m_host, false, r0, n, cudaMemcpyHostToDevice, s_in));
+        KM(kmajor((void*)dev->cholvec, io->cholvec_host, true, r0, n, cudaMemcpyHostToDevice, s_in));
         if (io->copy_static) {
             H2D(dev->tq + r0 * dims->Q, io->tq_host + r0 * dims->Q, n * dims->Q * D, s_in);
             H2D(dev->wq + r0 * dims->Q, io->wq_host + r0 * dims->Q, n * dims->Q * D, s_in);
@@ -508,9 +530,15 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
             H2D(dev->spike_t + s0, io->spike_t_host + s0, (size_t)(s1 - s0) * D, s_in);
         }
         if (hp) cudaEventRecord(hp->copied[b], s_in);
-    }
+        return SVGPFA_OK;
+    };
+    // the copies of block b + 1 are enqueued before the kernels of block b, so the host never runs far ahead of
+    // the device with copy calls only
+    rc = copy_in(0);
+    if (rc) return rc;
     for (int b = 0; b < nb; ++b) {
         const size_t r0 = r_of(b), r1 = r_of(b + 1), n = r1 - r0;
+        if (b + 1 < nb) { rc = copy_in(b + 1); if (rc) return rc; }
         svgpfa_dims db = *dims;
         db.r0 = (int32_t)r0;
         db.rn = nb > 1 ? (int32_t)n : 0;
@@ -524,17 +552,14 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
             cudaStreamWaitEvent(s_out, hp->done[b], 0);
         }
         if (nb > 1) {                              // this block's per-trial gradients
-            for (int k = 0; k < dims->K; ++k) {
-                const svgpfa_latent_desc& ds = dims->desc_host[k];
-                const size_t om = R * ds.moff + r0 * ds.M, op = R * ds.poff + r0 * ds.P;
-                if (flags & SVGPFA_GRAD_INDLOCS) D2H(io->gZ_host ? io->gZ_host + om : nullptr, dev->gZ + om, n * ds.M * D, s_out);
-                if (flags & SVGPFA_GRAD_POSTERIOR) {
-                    D2H(io->gm_host ? io->gm_host + om : nullptr, dev->gm + om, n * ds.M * D, s_out);
-                    D2H(io->gcholvec_host ? io->gcholvec_host + op : nullptr, dev->gcholvec + op, n * ds.P * D, s_out);
-                }
+            if (flags & SVGPFA_GRAD_INDLOCS) KM(kmajor(io->gZ_host, dev->gZ, false, r0, n, cudaMemcpyDeviceToHost, s_out));
+            if (flags & SVGPFA_GRAD_POSTERIOR) {
+                KM(kmajor(io->gm_host, dev->gm, false, r0, n, cudaMemcpyDeviceToHost, s_out));
+                KM(kmajor(io->gcholvec_host, dev->gcholvec, true, r0, n, cudaMemcpyDeviceToHost, s_out));
             }
         }
     }
+#undef KM
     rc = svgpfa_finalize(dims, dev, flags_run, stream);
     if (nb == 1) stage_mark(1 + SVGPFA_STAGE_FINALIZE, st);
     if (rc) return rc;

@@ -5,6 +5,8 @@
 //   indpoints_bwd_kernel  adjoints through alpha, c, X, KL and the Cholesky factorisation
 // Reference arithmetic: stats/kernelsMatricesStore.py:107-138, utils/miscUtils.py:135-155,209-216,
 // stats/klDivergence.py:31-44; adjoints per SURVEY.md Appendix A (the reference uses autograd).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -78,6 +80,113 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
         double s = 0.0;
         for (int i = 0; i < M; ++i) s += log(A[i * ld + i]);
         bf.logdetL[(size_t)r * dm.K + k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// M <= 32: one WARP per (trial, latent) matrix, rows in registers.
+// The kernel above keeps the matrix in shared memory (two loads per FMA, one thread per row or column) and needed
+// ~110 k cycles per matrix (ncu: 45 % fixed-latency "wait" stalls, 36 % of the samples in the column-wise inverse).
+// Here lane i owns ROW i of the trailing matrix in registers: a right-looking Cholesky whose column broadcasts are warp
+// shuffles, written with a rotating register window (after column j is eliminated a[k-1] <- a[k] - l_ij l_kj, so the
+// loop over j stays rolled and the code small), followed by the column-wise inverse with lane c owning column c of
+// L^-1 in registers and the entries of L read as warp-uniform (broadcast) shared-memory loads.  No block barriers.
+constexpr int KC_WARPS = 4;
+constexpr int KC_LD = 33;                         // odd: lane <-> row accesses are bank-conflict free
+constexpr int KC_WSM = 32 * KC_LD + 32;           // doubles of shared memory per warp: matrix + 1 / L_jj
+
+// 8 columns of the factorisation on a window of LEN columns (LEN = 32 - j0)
+template <int LEN>
+__device__ __forceinline__ void chol_stage(double (&a)[32], int j0, int lane, int M, double* __restrict__ A,
+                                           double* __restrict__ dinv, bool& bad, double& mydiag) {
+#pragma unroll 1
+    for (int j = j0; j < j0 + 8; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[0], j);
+        if (j < M && !(d > 0.0)) bad = true;
+        const double dg = sqrt(d), inv = 1.0 / dg;
+        const double lij = lane == j ? dg : (lane > j ? a[0] * inv : 0.0);
+        if (lane == j) mydiag = dg;
+        A[lane * KC_LD + j] = lij;
+        if (lane == 0) dinv[j] = inv;
+#pragma unroll
+        for (int kk = 1; kk < LEN; ++kk) {
+            const double lkj = __shfl_sync(0xffffffffu, lij, (j + kk) & 31);
+            a[kk - 1] = fma(-lij, lkj, a[kk]);           // columns past the matrix edge carry garbage, never read
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * KC_WARPS) kzz_chol_warp_kernel(svgpfa_dims dm, svgpfa_buffers bf, int nprob) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prob = blockIdx.x * KC_WARPS + warp;
+    if (prob >= nprob) return;                        // whole warps leave; there is no block barrier below
+    const int rl = prob / dm.K, k = prob - rl * dm.K, r = dm.r0 + rl;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const int M = ds.M;
+    double* A = sm + (size_t)warp * KC_WSM;
+    double* dinv = A + 32 * KC_LD;
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+    const double zi = lane < M ? bf.Z[(size_t)dm.R * ds.moff + (size_t)r * M + lane] : 0.0;
+    // Kzz (lower triangle) -> A; rows / columns >= M are those of the identity.  Rows t and 30 - t together hold 32
+    // lower-triangle entries, so 17 passes cover the 528 entries with (almost) every lane busy.
+    for (int t = 0; t < 17; ++t) {
+        int i, j;
+        if (t < 15) { i = lane <= t ? t : 30 - t; j = lane <= t ? lane : lane - t - 1; }
+        else if (t == 15) { i = 15; j = lane; }
+        else { i = 31; j = lane; }
+        const double z1 = __shfl_sync(0xffffffffu, zi, i), z2 = __shfl_sync(0xffffffffu, zi, j & 31);
+        if (j <= i) {
+            double v = i == j ? 1.0 : 0.0;
+            if (i < M && j < M) v = kappa_val(kc, z1 - z2) + (i == j ? dm.reg : 0.0);
+            A[i * KC_LD + j] = v;
+        }
+    }
+    __syncwarp();
+    double a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = j <= lane ? A[lane * KC_LD + j] : 0.0;
+    __syncwarp();
+    bool bad = false;
+    double mydiag = 1.0;
+    chol_stage<32>(a, 0, lane, M, A, dinv, bad, mydiag);
+    chol_stage<24>(a, 8, lane, M, A, dinv, bad, mydiag);
+    chol_stage<16>(a, 16, lane, M, A, dinv, bad, mydiag);
+    chol_stage<8>(a, 24, lane, M, A, dinv, bad, mydiag);
+    __syncwarp();
+    if (bad && lane == 0) {
+        if (atomicCAS(bf.info, 0, SVGPFA_INFO_NOT_PD) == 0) { bf.info[1] = r; bf.info[2] = k; }
+    }
+    double* Lg = bf.L + (size_t)r * dm.MM + ds.mmoff;
+    double* Lig = bf.Li + (size_t)r * dm.MM + ds.mmoff;
+    for (int idx = lane; idx < M * M; idx += 32) {
+        const int i = idx / M, j = idx - i * M;
+        Lg[idx] = A[i * KC_LD + j];                   // zeros above the diagonal
+    }
+    const double ld = warp_sum(lane < M ? log(mydiag) : 0.0);
+    if (lane == 0) bf.logdetL[(size_t)r * dm.K + k] = ld;
+    // L^-1: lane c owns column c;  x_i = (delta_ic - sum_{p < i} L_ip x_p) / L_ii  (x_p = 0 for p < c by itself)
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int p = 0; p < i; ++p) {
+            const double l = A[i * KC_LD + p];
+            if ((p & 3) == 0) s0 = fma(-l, x[p], s0);
+            else if ((p & 3) == 1) s1 = fma(-l, x[p], s1);
+            else if ((p & 3) == 2) s2 = fma(-l, x[p], s2);
+            else s3 = fma(-l, x[p], s3);
+        }
+        x[i] = ((s0 + s1) + (s2 + s3)) * dinv[i];
+    }
+    __syncwarp();                                     // every lane is done reading L
+#pragma unroll
+    for (int i = 0; i < 32; ++i) A[i * KC_LD + lane] = x[i];
+    __syncwarp();
+    for (int idx = lane; idx < M * M; idx += 32) {
+        const int i = idx / M, j = idx - i * M;
+        Lig[idx] = j <= i ? A[i * KC_LD + j] : 0.0;
     }
 }
 
@@ -332,7 +441,13 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M || dims->Mmax < 1) return svgpfa_set_error(SVGPFA_E_ARG, "kzz_chol_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 2, 2);
-    if (dims->Mmax <= 32) {
+    static int variant = -1;                        // SVGPFA_CHOL_VARIANT=1: the shared-memory kernel also for M <= 32
+    if (variant < 0) { const char* e = getenv("SVGPFA_CHOL_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (dims->Mmax <= 32 && variant != 1) {
+        const int nprob = svgpfa_ntrials(dims) * dims->K;
+        const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
+        kzz_chol_warp_kernel<<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
+    } else if (dims->Mmax <= 32) {
         cudaFuncSetAttribute(kzz_chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kzz_chol_kernel<true><<<dim3(svgpfa_ntrials(dims), dims->K), 32, smem, (cudaStream_t)stream>>>(*dims, *buf);
     } else {
