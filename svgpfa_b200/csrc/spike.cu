@@ -130,6 +130,28 @@ __device__ __forceinline__ PairInfo pair_info(const svgpfa_dims& dm, const svgpf
     return p;
 }
 
+// Lane slots of spike_tile_kernel: the pairs of the exponential-quadratic latents first, then -- starting at a CTA
+// boundary -- those of the periodic latents, so that every CTA (whose warps share the spike tile and meet at its
+// barriers) evaluates ONE kernel type: a periodic evaluation costs ~2.5x an exponential-quadratic one, and a warp whose
+// lanes mix the types runs both loops one after the other.  Returns the storage index moff_k + j of the first of the
+// np pairs of (warp group grp, lane), or a value >= KM for an idle lane.
+__device__ __forceinline__ int slot_to_pair(const svgpfa_dims& dm, const svgpfa_buffers& bf, int grp, int lane, int np,
+                                            int wpb) {
+    int n_eq = 0;
+    for (int k = 0; k < dm.K; ++k) n_eq += bf.desc[k].ktype == SVGPFA_KERNEL_PERIODIC ? 0 : bf.desc[k].M;
+    const int eq_warps = ((n_eq + 32 * np - 1) / (32 * np) + wpb - 1) / wpb * wpb;
+    const bool per = grp >= eq_warps;
+    int rem = ((per ? grp - eq_warps : grp) * 32 + lane) * np;
+    if (rem >= (per ? dm.KM - n_eq : n_eq)) return dm.KM;
+    for (int k = 0; k < dm.K; ++k) {
+        const svgpfa_latent_desc ds = bf.desc[k];
+        if ((ds.ktype == SVGPFA_KERNEL_PERIODIC) != per) continue;
+        if (rem < ds.M) return ds.moff + rem;
+        rem -= ds.M;
+    }
+    return dm.KM;
+}
+
 // NP = (latent, inducing point) pairs per lane: slot p of a warp covers pairs grp*32*NP + p*32 + lane, so the
 // spike load, the loop and the segment bookkeeping are shared by NP kernel evaluations.
 // UNROLL = spikes per software-pipelined iteration, MINB = resident CTAs per SM asked of ptxas.
@@ -259,7 +281,28 @@ __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa
 // resident warps hide latency and emits the evaluations of an iteration as one dependency chain after the other.
 constexpr int ST_TILE = 1024;
 constexpr int ST_MAX_WPB = 8;
-constexpr unsigned ST_SMEM = SVGPFA_EXP2M_TAB_BYTES + 8 * (ST_TILE + 2 * ST_MAX_WPB);
+constexpr int ST_SLOTS = 8;                                   // deferred dC reductions per warp
+constexpr int ST_DCW = ST_SLOTS * 33 + ST_SLOTS / 2;          // doubles per warp: [slot][33] values + neuron ids
+constexpr unsigned ST_SMEM = SVGPFA_EXP2M_TAB_BYTES + 8 * (ST_TILE + 2 * ST_MAX_WPB + ST_MAX_WPB * ST_DCW) + 16384;
+
+// dC of up to ST_SLOTS finished segments of a single-latent warp: slot rows [slot][lane] hold alpha_j * sum kappa;
+// lane (slot = lane & 7, part = lane >> 3) adds 8 entries of its row, two shuffles join the four parts, and lane
+// `slot` issues the one atomic of the segment.  ~3 instructions per segment instead of a 5-step segmented warp
+// reduction per segment (the flush was 14 % of the kernel's stall samples).
+__device__ __forceinline__ void drain_dc(const double* __restrict__ dcb, const int* __restrict__ dcn, int cnt, int lane,
+                                         double* __restrict__ gCk, int K) {
+    __syncwarp();
+    const int sl = lane & 7, part = lane >> 3;
+    double sum = 0.0;
+    const double* row = dcb + sl * 33 + 8 * part;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += row[e];
+    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    if (part == 0 && sl < cnt) atomicAdd(gCk + (size_t)dcn[sl] * K, sum);
+    __syncwarp();
+}
+
 
 // U spikes x NP pairs = NE independent evaluations, stage by stage (svgpfa_exp2m_n)
 template <bool KGRAD, bool CLAMP, int U, int NP>
@@ -318,45 +361,104 @@ __device__ __forceinline__ void eq_run(const double* __restrict__ tp, int cnt, d
 
 // periodic pairs: w = sin(pi d/p) sc with sc = sqrt(256 * 2 / ln2) / l;  p1 += kappa sin(2 pi d/p),
 // p2 += kappa w^2 (rescaled by 1/sc^2 at the end), p3 += kappa sin(2 pi d/p) d
+// sin and cos of 2 pi x by table: n = rint(64 x), u = 64 x - n in [-1/2, 1/2], theta = 2 pi u / 64 (|theta| <= 0.0491),
+//   sin(2 pi x) = S_n cos(theta) + C_n sin(theta),  cos(2 pi x) = C_n cos(theta) - S_n sin(theta)
+// with (S_n, C_n) = sincos(2 pi n / 64) in shared memory (64 entries x 16 replicas, conflict-free like the exp table) and
+// Taylor polynomials of degree 7 / 8 in theta (truncation < 5e-18).  19 FP64 instructions against ~40 (+ ~20 others) of
+// libdevice's sincospi, which computes a full-range sine AND cosine polynomial.
+constexpr int ST_SC_ENTRIES = 64;
+constexpr int ST_SC_DOUBLES = 2 * ST_SC_ENTRIES * SVGPFA_EXP2M_REP;        // 16 KB
+
+__device__ __forceinline__ void load_sincos_tab(double2* tab) {
+    for (int i = threadIdx.x; i < ST_SC_ENTRIES * SVGPFA_EXP2M_REP; i += blockDim.x) {
+        double sv, cv;
+        sincospi((double)(i / SVGPFA_EXP2M_REP) * (2.0 / ST_SC_ENTRIES), &sv, &cv);
+        tab[i] = make_double2(sv, cv);
+    }
+}
+
+__device__ __forceinline__ void sincos2pi_tab(double x64, const double2* __restrict__ lane_sc, double& sv, double& cv) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = x64 + MAGIC;
+    const double u = x64 - (t - MAGIC);
+    const int n = __double2loint(t) & (ST_SC_ENTRIES - 1);
+    const double th = u * (2.0 * SVGPFA_PI / ST_SC_ENTRIES), th2 = th * th;
+    double ps = fma(th2, -1.0 / 5040.0, 1.0 / 120.0);
+    ps = fma(th2, ps, -1.0 / 6.0);
+    const double st = fma(th * th2, ps, th);                  // sin(theta)
+    double pc = fma(th2, 1.0 / 40320.0, -1.0 / 720.0);
+    pc = fma(th2, pc, 1.0 / 24.0);
+    pc = fma(th2, pc, -0.5);
+    const double ct = fma(th2, pc, 1.0);                      // cos(theta)
+    const double2 sc = lane_sc[n * SVGPFA_EXP2M_REP];
+    sv = fma(sc.x, ct, sc.y * st);
+    cv = fma(sc.y, ct, -sc.x * st);
+}
+
+// kappa = s2 exp(nh sin^2(pi d/p)) with sin^2 = (1 - cos(2 pi d/p)) / 2;  hsc2 = sc^2 / 2, invp64 = 64 / p
+template <bool KGRAD>
+__device__ __forceinline__ void per_eval(double t, double hsc2, double zc, double invp64, unsigned etab,
+                                         const double2* __restrict__ lane_sc, double& pn, double& p1, double& p2,
+                                         double& p3) {
+    const double dl = t - zc;
+    double s2x, c2x;
+    sincos2pi_tab(dl * invp64, lane_sc, s2x, c2x);
+    const double w2 = fabs((1.0 - c2x) * hsc2);               // |.|: a rounding-level negative value must not look huge to the clamp
+    const double kv = svgpfa_exp2m(svgpfa_exp2m_clamp(w2), etab);
+    pn += kv;
+    if (KGRAD) {
+        const double ww = kv * s2x;
+        p1 += ww;
+        p2 = fma(kv, w2, p2);
+        p3 = fma(ww, dl, p3);
+    }
+}
+
+// two spikes per iteration: the sincos + exp chain is ~35 dependent FP64 instructions, so a second independent
+// chain per lane roughly halves the exposed latency (config #3 ran at ~400 cycles per periodic warp evaluation with
+// libdevice's sincospi and one spike per iteration)
 template <bool KGRAD, int NP>
 __device__ __forceinline__ void per_run(const double* __restrict__ tp, int cnt, double sc, const double (&zc)[NP],
-                                        double invp, unsigned etab, double (&pn)[NP], double (&p1)[NP],
-                                        double (&p2)[NP], double (&p3)[NP]) {
+                                        double invp, unsigned etab, const double2* __restrict__ lane_sc,
+                                        double (&pn)[NP], double (&p1)[NP], double (&p2)[NP], double (&p3)[NP]) {
+    const double hsc2 = 0.5 * sc * sc, invp64 = invp * ST_SC_ENTRIES;
+    int i = 0;
 #pragma unroll 1
-    for (int i = 0; i < cnt; ++i) {
-        const double t = tp[i];
+    for (; i + 2 <= cnt; i += 2) {
+        const double t0 = tp[i], t1 = tp[i + 1];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-            const double dl = t - zc[p];
-            double sn, cs;
-            sincospi(dl * invp, &sn, &cs);
-            const double w = sn * sc;
-            const double w2 = w * w;
-            const double kv = svgpfa_exp2m(svgpfa_exp2m_clamp(w2), etab);
-            pn[p] += kv;
-            if (KGRAD) {
-                const double ww = kv * (2.0 * sn * cs);
-                p1[p] += ww;
-                p2[p] = fma(kv, w2, p2[p]);
-                p3[p] = fma(ww, dl, p3[p]);
-            }
+            double qn = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;               // second chain, joined below
+            per_eval<KGRAD>(t0, hsc2, zc[p], invp64, etab, lane_sc, pn[p], p1[p], p2[p], p3[p]);
+            per_eval<KGRAD>(t1, hsc2, zc[p], invp64, etab, lane_sc, qn, q1, q2, q3);
+            pn[p] += qn; p1[p] += q1; p2[p] += q2; p3[p] += q3;
         }
+    }
+    if (i < cnt) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) per_eval<KGRAD>(tp[i], hsc2, zc[p], invp64, etab, lane_sc, pn[p], p1[p], p2[p], p3[p]);
     }
 }
 
 template <bool KGRAD, int NP, int MAXT, int MAXR>
 __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
-                                                                int n_chunks, int chunk) {
+                                                                int n_chunks, int chunk, int has_periodic) {
     extern __shared__ __align__(16) double st_smem[];       // ST_SMEM bytes: table | spike tile | min/max scratch
     double* ts = st_smem + SVGPFA_EXP2M_TAB_BYTES / 8;
     double* red = ts + ST_TILE;
+    double* dcb = red + 2 * ST_MAX_WPB + (threadIdx.x >> 5) * ST_DCW;          // this warp's deferred-dC rows
+    int* dcn = reinterpret_cast<int*>(dcb + ST_SLOTS * 33);
+    // sincos table of the periodic kernels, after the per-warp rows (allocated only when a latent is periodic)
+    double2* sctab = reinterpret_cast<double2*>(red + 2 * ST_MAX_WPB + (blockDim.x >> 5) * ST_DCW);
+    if (has_periodic) load_sincos_tab(sctab);
+    const double2* lane_sc = sctab + (threadIdx.x & (SVGPFA_EXP2M_REP - 1));
     svgpfa_load_exp2m_tab(st_smem);
     const unsigned etab = svgpfa_exp2m_lane_tab(st_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
     const int grp = blockIdx.y * wpb + warp;
     // a warp past the last pair still takes part in the staging and the barriers; its lanes are inactive
-    const PairInfo pi = pair_info(dm, bf, (grp * 32 + lane) * NP, lane);       // first pair of the lane
+    const PairInfo pi = pair_info(dm, bf, slot_to_pair(dm, bf, grp, lane, NP, wpb), lane);   // first pair of the lane
     const svgpfa_latent_desc ds = bf.desc[pi.k];
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi.k);
     const bool per = kc.type == SVGPFA_KERNEL_PERIODIC;
@@ -369,7 +471,11 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgp
         a[p] = pi.active ? kc.s2 * bf.alpha[(size_t)r * dm.KM + l] : 0.0;     // scale^2 alpha_j
     }
     const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
-    const bool warp_live = grp * 32 * NP < dm.KM;
+    const bool warp_live = __any_sync(0xffffffffu, pi.active);
+    // all 32 lanes active and on the same latent (M_k a multiple of 32 / NP): dC reductions are deferred
+    const int k_lane0 = __shfl_sync(0xffffffffu, pi.k, 0);       // (not inside the && below: every lane must shuffle)
+    const bool one_latent = __all_sync(0xffffffffu, pi.active && pi.k == k_lane0);
+    int slot = 0;
     const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
     const int64_t* __restrict__ seg = bf.seg_off + (size_t)r * dm.N;
     const double* __restrict__ st = bf.spike_t;
@@ -426,7 +532,7 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgp
             const int64_t e = min(seg_end, tile1);
             const int cnt = (int)(e - pos);
             const double* tp = ts + (int)(pos - tile0);
-            if (per) per_run<KGRAD, NP>(tp, cnt, sc, zc, kc.invp, etab, pn, p1, p2, p3);
+            if (per) per_run<KGRAD, NP>(tp, cnt, sc, zc, kc.invp, etab, lane_sc, pn, p1, p2, p3);
             else if (clamp) eq_run<KGRAD, true, NP>(tp, cnt, sc, zs, etab, pn, p1, p2);
             else eq_run<KGRAD, false, NP>(tp, cnt, sc, zs, etab, pn, p1, p2);
             __syncwarp();
@@ -445,13 +551,23 @@ __global__ void __launch_bounds__(MAXT) __maxnreg__(MAXR) spike_tile_kernel(svgp
                     pn[p] = p1[p] = p2[p] = p3[p] = 0.0;
                 }
                 if (need_emb) {
-                    v = seg_sum(v, pi.same);
-                    if (pi.head) atomicAdd(gC + (size_t)n * dm.K, v);
+                    if (one_latent) {
+                        dcb[slot * 33 + lane] = v;
+                        if (lane == 0) dcn[slot] = n;
+                        if (++slot == ST_SLOTS) {
+                            drain_dc(dcb, dcn, ST_SLOTS, lane, gC, dm.K);
+                            slot = 0;
+                        }
+                    } else {
+                        v = seg_sum(v, pi.same);
+                        if (pi.head) atomicAdd(gC + (size_t)n * dm.K, v);
+                    }
                 }
             }
         }
     }
     if (!warp_live) return;
+    if (slot) drain_dc(dcb, dcn, slot, lane, gC, dm.K);
     const double isc = 1.0 / sc;
     double t0s = 0.0, t1s = 0.0;
 #pragma unroll
@@ -574,15 +690,23 @@ __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm
 // Grid of the spike kernels: warps of 32 * np pairs, wpb warps per CTA (the value in [min_wpb, max_wpb] that leaves
 // the fewest idle warps), and enough CTAs to fill the machine a few times over (every trial's neurons are split into
 // n_chunks ranges when R alone does not provide them).
-static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, int max_wpb, dim3* grid, int* wpb_out,
-                       int* n_chunks_out, int* chunk_out) {
-    const int LG = (dims->KM + 32 * np - 1) / (32 * np);
-    int wpb = LG < min_wpb ? LG : min_wpb, best = 1 << 30;
+static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, int max_wpb, bool by_type, dim3* grid,
+                       int* wpb_out, int* n_chunks_out, int* chunk_out) {
+    // warp groups: by_type (spike_tile_kernel) = those of the exponential-quadratic pairs, rounded up to whole CTAs,
+    // then those of the periodic pairs (slot_to_pair); otherwise ceil(KM / (32 np))
+    int n_eq = 0;
+    for (int k = 0; k < dims->K; ++k)
+        n_eq += (by_type && dims->desc_host[k].ktype == SVGPFA_KERNEL_PERIODIC) ? 0 : dims->desc_host[k].M;
+    const int lg_eq = (n_eq + 32 * np - 1) / (32 * np), lg_per = (dims->KM - n_eq + 32 * np - 1) / (32 * np);
+    auto warps_for = [&](int w) { return (lg_eq + w - 1) / w * w + (lg_per + w - 1) / w * w; };
+    const int LG = lg_eq + lg_per;
+    int wpb = LG < min_wpb ? (LG > 0 ? LG : 1) : min_wpb, best = 1 << 30;
+    if (lg_eq && lg_per && wpb < min_wpb) wpb = lg_eq > lg_per ? lg_eq : lg_per;
     for (int w = min_wpb; w <= max_wpb && LG >= min_wpb; ++w) {
-        const int waste = (LG + w - 1) / w * w - LG;
+        const int waste = warps_for(w) - LG;
         if (waste < best) { best = waste; wpb = w; }
     }
-    const int gy = (LG + wpb - 1) / wpb;
+    const int gy = warps_for(wpb) / wpb;
     const long target_warps = (long)nsm * 64 * 4 / np;
     const long Rn = svgpfa_ntrials(dims);
     long n_chunks = (target_warps + Rn * LG - 1) / (Rn * LG);
@@ -597,9 +721,9 @@ static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, in
 }
 
 // SVGPFA_SPIKE_VARIANT (environment, experiments only): 1 = the register/global-load kernel (spike_fwd_bwd_kernel);
-// 12 = spike_tile_kernel with 2 pairs per lane, 111 = 1 pair per lane with a 128-register budget; default = 1 pair
-// per lane, 96 registers.  Measured on B200, config #5 shard of 2000 trials (ms): 1 -> 17.16, default -> 15.90,
-// 111 -> 15.80, 12 -> 16.43, 4 pairs per lane -> 18.4 (dropped).
+// 12 = spike_tile_kernel with 2 pairs per lane, 96 = 1 pair per lane with a 96-register budget; default = 1 pair
+// per lane, 128 registers (4 CTAs per SM).  Measured on B200, config #5 shard of 2000 trials (ms): 1 -> 17.16,
+// 96 -> 15.92, default -> 15.22, 12 -> 16.43, 4 pairs per lane -> 18.4 (dropped).
 static int spike_variant() {
     static int v = -1;
     if (v < 0) {
@@ -620,9 +744,13 @@ static void launch_tile(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint
     }
     dim3 grid;
     int wpb, n_chunks, chunk;
-    spike_grid(dims, nsm, NP, MAXT >= 256 ? 4 : (MAXT / 32 < 4 ? MAXT / 32 : 4), MAXT / 32, &grid, &wpb, &n_chunks, &chunk);
-    if (kgrad) spike_tile_kernel<true, NP, MAXT, MAXR><<<grid, 32 * wpb, ST_SMEM, st>>>(*dims, *buf, flags, n_chunks, chunk);
-    else spike_tile_kernel<false, NP, MAXT, MAXR><<<grid, 32 * wpb, ST_SMEM, st>>>(*dims, *buf, flags, n_chunks, chunk);
+    spike_grid(dims, nsm, NP, MAXT >= 256 ? 4 : (MAXT / 32 < 4 ? MAXT / 32 : 4), MAXT / 32, true, &grid, &wpb, &n_chunks, &chunk);
+    int has_periodic = 0;
+    for (int k = 0; k < dims->K; ++k) has_periodic |= dims->desc_host[k].ktype == SVGPFA_KERNEL_PERIODIC;
+    const size_t smem = SVGPFA_EXP2M_TAB_BYTES + 8 * (size_t)(ST_TILE + 2 * ST_MAX_WPB + wpb * ST_DCW) +
+                        (has_periodic ? 16384 : 0);
+    if (kgrad) spike_tile_kernel<true, NP, MAXT, MAXR><<<grid, 32 * wpb, smem, st>>>(*dims, *buf, flags, n_chunks, chunk, has_periodic);
+    else spike_tile_kernel<false, NP, MAXT, MAXR><<<grid, 32 * wpb, smem, st>>>(*dims, *buf, flags, n_chunks, chunk, has_periodic);
 }
 
 extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
@@ -638,7 +766,7 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     if (var == 1) {     // measured on B200, config #5 shard of 2000 trials: 17.1 ms (profiles/README.md)
         dim3 grid;
         int wpb, n_chunks, chunk;
-        spike_grid(dims, nsm, 1, SP_WPB, SP_WPB, &grid, &wpb, &n_chunks, &chunk);
+        spike_grid(dims, nsm, 1, SP_WPB, SP_WPB, false, &grid, &wpb, &n_chunks, &chunk);
         grid.y = ((dims->KM + 31) / 32 + SP_WPB - 1) / SP_WPB;
         if (kgrad) spike_fwd_bwd_kernel<true, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
         else spike_fwd_bwd_kernel<false, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
@@ -647,8 +775,8 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
         bool even = true;
         for (int k = 0; k < dims->K; ++k) even = even && (dims->desc_host[k].M % 2 == 0);
         if (var == 12 && even) launch_tile<2, 160, 96>(dims, buf, flags, st, nsm, kgrad);
-        else if (var == 111) launch_tile<1, 128, 128>(dims, buf, flags, st, nsm, kgrad);
-        else launch_tile<1, 128, 96>(dims, buf, flags, st, nsm, kgrad);
+        else if (var == 96) launch_tile<1, 128, 96>(dims, buf, flags, st, nsm, kgrad);
+        else launch_tile<1, 128, 128>(dims, buf, flags, st, nsm, kgrad);
     }
     SVGPFA_CHECK_LAUNCH("spike_fwd_bwd");
     return SVGPFA_OK;
