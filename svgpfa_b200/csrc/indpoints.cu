@@ -12,6 +12,8 @@
 namespace {
 
 constexpr int IP_THREADS = 128;
+constexpr int IP_BWD_THREADS = 256;          // 8 warps, two 8x8 output tiles per warp and product: 2.22 (128 threads) ->
+                                             // 1.71 ms on the 2000-trial shard; 512 threads 2.47 ms
 
 __device__ __forceinline__ int ld_of(int M) { return M | 1; }   // odd leading dimension: conflict-free columns
 
@@ -269,7 +271,7 @@ __device__ __forceinline__ void mm_mma(int MP, bool lower_only, FA a, FB b, FR r
     }
 }
 
-__global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+__global__ void __launch_bounds__(IP_BWD_THREADS) indpoints_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     extern __shared__ double sm[];
     __shared__ double red[32];
     const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
@@ -430,6 +432,12 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_bwd_kernel(svgpfa_dims d
     }
 }
 
+int ip_bwd_threads() {          // SVGPFA_IPBWD_THREADS (experiments): 128 or 256
+    static int t = 0;
+    if (!t) { const char* e = getenv("SVGPFA_IPBWD_THREADS"); t = e ? atoi(e) : IP_BWD_THREADS; if (t != 128 && t != 256) t = IP_BWD_THREADS; }
+    return t;
+}
+
 size_t ip_smem(int Mmax, int nmat, int nvec) {
     const int MP = (Mmax + 7) / 8 * 8, ld = MP + 4;      // covers both the odd-ld (M|1) and the padded (MP+4) layouts
     return sizeof(double) * ((size_t)nmat * MP * ld + (size_t)nvec * MP);
@@ -474,7 +482,7 @@ extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     const size_t smem = ip_smem(dims->Mmax, 6, 6);
     cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), ip_bwd_threads(), smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;
 }
