@@ -395,7 +395,7 @@ constexpr int EMM_THREADS = 256;
 __host__ __device__ inline int emm_kp(int K) { return (K + 1 + 7) / 8 * 8; }       // K + ones column, padded to 8
 __host__ __device__ inline size_t emm_smem_doubles(int K) {
     const int KP = emm_kp(K);
-    return (size_t)KP * EMM_TNS + (size_t)EMM_TQ * EMM_TNS + (size_t)2 * KP * EMM_LDQ + EMM_TQ + EMM_TN;
+    return (size_t)2 * KP * EMM_TNS + (size_t)EMM_TQ * EMM_TNS + (size_t)2 * KP * EMM_LDQ + EMM_TQ + EMM_TN;
 }
 
 template <int KT>      // KT = KP / 8 k-tiles
@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
     __shared__ double red[32];
     const int K = dm.K, N = dm.N, Q = dm.Q;
     double* CT = sm;                               // [KP][TNS]   C^T, rows >= K are zero
-    double* Gs = CT + (size_t)KP * TNS;            // [TQ][TNS]
+    double* CT2 = CT + (size_t)KP * TNS;           // [KP][TNS]   (C^T)^2 (keeps a DMUL and two selects out of GEMM B's loop)
+    double* Gs = CT2 + (size_t)KP * TNS;           // [TQ][TNS]
     double* muT = Gs + (size_t)EMM_TQ * TNS;       // [KP][LDQ]   row K = ones
     double* varT = muT + (size_t)KP * LDQ;         // [KP][LDQ]
     double* ws = varT + (size_t)KP * LDQ;          // [TQ]
@@ -417,7 +418,9 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
     const bool need_lat = flags & (SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
     for (int idx = tid; idx < KP * EMM_TN; idx += EMM_THREADS) {
         const int kk = idx / EMM_TN, nn = idx - kk * EMM_TN;
-        CT[kk * TNS + nn] = (kk < K && n0 + nn < N) ? bf.C[(size_t)(n0 + nn) * K + kk] : 0.0;
+        const double cval = (kk < K && n0 + nn < N) ? bf.C[(size_t)(n0 + nn) * K + kk] : 0.0;
+        CT[kk * TNS + nn] = cval;
+        CT2[kk * TNS + nn] = cval * cval;
     }
     if (tid < EMM_TN) dvec[tid] = (n0 + tid < N) ? bf.d[n0 + tid] : 0.0;
     // GEMM C accumulators: warp owns neuron tiles {2 warp, 2 warp + 1} x all k-tiles, for Mu and for Var
@@ -431,17 +434,38 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
     const int nitems = (dm.rn ? dm.rn : dm.R) * qtiles;
     const size_t part_off = (size_t)tile * dm.R * K * Q;
     __syncthreads();
+    // The statistics of the NEXT item are fetched into registers while the three products of the current one run
+    // (ncu: the in-loop global loads were 9 % of the stall samples, all threads waiting at the barrier behind them).
+    constexpr int NPF = (EMM_TQ * KP + EMM_THREADS - 1) / EMM_THREADS;
+    double pf_mu[NPF], pf_var[NPF], pf_w = 0.0;
+    auto fetch = [&](int it) {
+        const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EMM_TQ;
+#pragma unroll
+        for (int e = 0; e < NPF; ++e) {
+            const int idx = tid + e * EMM_THREADS;
+            const int qq = idx / KP, kk = idx - qq * KP;
+            const bool v = idx < EMM_TQ * KP && (q0 + qq) < Q && kk < K;
+            const size_t o = ((size_t)r * Q + q0 + qq) * K + kk;
+            pf_mu[e] = v ? bf.mu_q[o] : ((idx < EMM_TQ * KP && kk == K && (q0 + qq) < Q) ? 1.0 : 0.0);
+            pf_var[e] = v ? bf.var_q[o] : 0.0;
+        }
+        if (tid < EMM_TQ) pf_w = (q0 + tid < Q) ? bf.wq[(size_t)r * Q + q0 + tid] : 0.0;
+    };
+    if ((int)blockIdx.y < nitems) fetch(blockIdx.y);
     for (int it = blockIdx.y; it < nitems; it += gridDim.y) {
         const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EMM_TQ;
-        for (int idx = tid; idx < EMM_TQ * KP; idx += EMM_THREADS) {
-            const int qq = idx / KP, kk = idx - qq * KP;
-            const bool v = (q0 + qq) < Q && kk < K;
-            const size_t o = ((size_t)r * Q + q0 + qq) * K + kk;
-            muT[kk * LDQ + qq] = v ? bf.mu_q[o] : ((kk == K && (q0 + qq) < Q) ? 1.0 : 0.0);
-            varT[kk * LDQ + qq] = v ? bf.var_q[o] : 0.0;
+#pragma unroll
+        for (int e = 0; e < NPF; ++e) {
+            const int idx = tid + e * EMM_THREADS;
+            if (idx < EMM_TQ * KP) {
+                const int qq = idx / KP, kk = idx - qq * KP;
+                muT[kk * LDQ + qq] = pf_mu[e];
+                varT[kk * LDQ + qq] = pf_var[e];
+            }
         }
-        if (tid < EMM_TQ) ws[tid] = (q0 + tid < Q) ? bf.wq[(size_t)r * Q + q0 + tid] : 0.0;
+        if (tid < EMM_TQ) ws[tid] = pf_w;
         __syncthreads();
+        if (it + (int)gridDim.y < nitems) fetch(it + gridDim.y);
         // ---- GEMM A: h[qt][nl] = H[8 qt + g][8 (2 warp + nl) + 2 tg + e]
         {
             double h[2][2][2], sg[2][2][2];
@@ -463,13 +487,18 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
                     av[qt] = varT[(4 * ks + tg) * LDQ + 8 * qt + g];
                 }
 #pragma unroll
-                for (int nl = 0; nl < 2; ++nl) bc[nl] = CT[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+                double bc2[2];
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) {
+                    bc[nl] = CT[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+                    bc2[nl] = CT2[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+                }
 #pragma unroll
                 for (int qt = 0; qt < 2; ++qt)
 #pragma unroll
                     for (int nl = 0; nl < 2; ++nl) {
                         dmma(h[qt][nl][0], h[qt][nl][1], am[qt], bc[nl]);
-                        dmma(sg[qt][nl][0], sg[qt][nl][1], av[qt], bc[nl] * bc[nl]);
+                        dmma(sg[qt][nl][0], sg[qt][nl][1], av[qt], bc2[nl]);
                     }
             }
 #pragma unroll
@@ -493,12 +522,10 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
             for (int u = warp; u < 4 * KT; u += EMM_THREADS / 32) {
                 const int kind = u & 1, qt = (u >> 1) & 1, kt = u >> 2;
                 double c0 = 0.0, c1 = 0.0;
+                const double* ga = Gs + (8 * qt + g) * TNS + tg;
+                const double* cb = (kind ? CT2 : CT) + (8 * kt + g) * TNS + tg;
 #pragma unroll 8
-                for (int ks = 0; ks < EMM_TN / 4; ++ks) {
-                    const double a = Gs[(8 * qt + g) * TNS + 4 * ks + tg];
-                    const double b = CT[(8 * kt + g) * TNS + 4 * ks + tg];
-                    dmma(c0, c1, a, kind ? b * b : b);
-                }
+                for (int ks = 0; ks < EMM_TN / 4; ++ks) dmma(c0, c1, ga[4 * ks], cb[4 * ks]);
                 const int q = q0 + 8 * qt + g, kk = 8 * kt + 2 * tg;
                 if (q < Q) {
                     double* dst = kind ? bf.varbar_part : bf.mubar_part;
