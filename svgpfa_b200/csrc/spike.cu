@@ -710,6 +710,7 @@ static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, in
     const long target_warps = (long)nsm * 64 * 4 / np;
     const long Rn = svgpfa_ntrials(dims);
     long n_chunks = (target_warps + Rn * LG - 1) / (Rn * LG);
+    if (const char* e = getenv("SVGPFA_SPIKE_CHUNKS")) n_chunks = atol(e);     // tests: force long neuron ranges
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > dims->N) n_chunks = dims->N;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);

@@ -94,6 +94,23 @@ def test_inducing_point_counts_up_to_64(M_list, Q):
     assert worst[0] <= GRAD_TOL, worst
 
 
+@pytest.mark.parametrize("M,mixed", [(32, False), (20, True), (16, False)])
+def test_spike_tiles_and_segments_across_tile_boundaries(M, mixed, monkeypatch):
+    """The spike kernel stages 1024 spike times per shared-memory tile.  With the neuron range of a CTA forced to the
+    whole trial (~2400 spikes) every CTA walks several tiles, segments straddle tile boundaries, and (M = 32) the
+    deferred dC reduction drains several times -- against the oracle executed on the box."""
+    from oracle import svgpfa_oracle as orc
+    monkeypatch.setenv("SVGPFA_SPIKE_CHUNKS", "1")
+    cfg = dict(R=2, N=120, K=2, M=M, Q=16, mixed=mixed, ragged=False)
+    case = synthetic.make_case(cfg, seed=5, reg=1e-3)
+    assert case["spike_counts"].sum(axis=1).min() > 2048
+    ref = orc.elbo_and_grads(case)
+    _, out = _eval_all(case)
+    assert abs(out["elbo"] - ref["elbo"]) <= ELBO_TOL * abs(ref["elbo"])
+    worst = max((rel_err(out[key], ref[key]), key) for key in _grad_keys(2))
+    assert worst[0] <= GRAD_TOL, worst
+
+
 @pytest.mark.parametrize("groups", [dict(posterior=True, embedding=False, kernels=False, indlocs=False),
                                     dict(posterior=False, embedding=True, kernels=False, indlocs=False),
                                     dict(posterior=False, embedding=False, kernels=True, indlocs=False),
