@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
+LIB_PATH = os.environ.get("SVGPFA_LIB") or os.path.join(PKG, "libsvgpfa_b200.so")   # SVGPFA_LIB: experiments only
 
 ABI_VERSION = 2
 MAX_M = 64

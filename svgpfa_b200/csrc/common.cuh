@@ -98,7 +98,8 @@ __device__ __forceinline__ double svgpfa_exp2m(double w2, unsigned lane_tab) {
 #define SVGPFA_PIN4(x) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]))
 template <int NE>
 __device__ __forceinline__ void svgpfa_pin(double (&x)[NE]) {
-    if constexpr (NE == 4) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]));
+    if constexpr (NE == 8) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]), "+d"(x[4]), "+d"(x[5]), "+d"(x[6]), "+d"(x[7]));
+    else if constexpr (NE == 4) asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]));
     else if constexpr (NE == 2) asm volatile("" : "+d"(x[0]), "+d"(x[1]));
     else asm volatile("" : "+d"(x[0]));
 }

@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa
 // NP > 1 requires every M_k to be a multiple of NP (all pairs of a lane then share the latent).
 // Register budget: __maxnreg__ instead of a min-blocks launch bound -- with a min-blocks hint ptxas assumes the
 // resident warps hide latency and emits the evaluations of an iteration as one dependency chain after the other.
+#ifndef ST_U1
+#define ST_U1 8       // spikes per iteration with one pair per lane; measured on the 2000-trial shard: 2 -> 16.04 ms,
+#endif                // 4 -> 14.43, 8 -> 14.05 (compile with -DST_U1=... to compare)
 constexpr int ST_TILE = 1024;
 constexpr int ST_MAX_WPB = 8;
 constexpr int ST_SLOTS = 8;                                   // deferred dC reductions per warp
@@ -335,11 +338,12 @@ __device__ __forceinline__ void eq_eval_n(const double (&t)[U], double sc, const
     }
 }
 
-// cnt spikes (warp-uniform shared-memory reads) against the NP pairs of the lane; 4 / NP spikes per iteration
+// cnt spikes (warp-uniform shared-memory reads) against the NP pairs of the lane; U spikes per iteration, then
+// remainders of 4, 2 and 1
 template <bool KGRAD, bool CLAMP, int NP>
 __device__ __forceinline__ void eq_run(const double* __restrict__ tp, int cnt, double sc, const double (&zs)[NP],
                                        unsigned etab, double (&pn)[NP], double (&p1)[NP], double (&p2)[NP]) {
-    constexpr int U = 4 / NP;
+    constexpr int U = NP == 1 ? ST_U1 : 4 / NP;
     const double* const pe = tp + (cnt - cnt % U);
 #pragma unroll 1
     for (; tp != pe; tp += U) {
@@ -348,7 +352,12 @@ __device__ __forceinline__ void eq_run(const double* __restrict__ tp, int cnt, d
         for (int u = 0; u < U; ++u) t[u] = tp[u];
         eq_eval_n<KGRAD, CLAMP, U, NP>(t, sc, zs, etab, pn, p1, p2);
     }
-    if (U == 4 && (cnt & 2)) {
+    if (U == 8 && (cnt & 4)) {
+        const double t[4] = {tp[0], tp[1], tp[2], tp[3]};
+        eq_eval_n<KGRAD, CLAMP, 4, NP>(t, sc, zs, etab, pn, p1, p2);
+        tp += 4;
+    }
+    if (U >= 4 && (cnt & 2)) {
         const double t[2] = {tp[0], tp[1]};
         eq_eval_n<KGRAD, CLAMP, 2, NP>(t, sc, zs, etab, pn, p1, p2);
         tp += 2;
