@@ -23,7 +23,7 @@ import warnings
 import numpy as np
 import torch
 
-from . import _cabi, sharding
+from . import _cabi, ingest, sharding
 from .kernels import kernel_spec
 
 _F64 = torch.float64
@@ -198,21 +198,7 @@ class B200SVLowerBound:
         """``measurements[r][n]`` = spike times of neuron n in trial r (list / array / tensor, float32
         or float64).  Stacked trial-major, neuron-major, within-neuron order kept -- the order of
         ``PointProcessELL.__stackSpikeTimes`` (stats/expectedLogLikelihood.py:157-173)."""
-        R = len(measurements)
-        N = len(measurements[0]) if R else 0
-        counts = np.zeros((R, N), dtype=np.int64)
-        pieces = []
-        for r in range(R):
-            if len(measurements[r]) != N:
-                raise ValueError("every trial must list the same number of neurons")
-            for n in range(N):
-                s = measurements[r][n]
-                s = s.detach().cpu().numpy() if isinstance(s, torch.Tensor) else np.asarray(s)
-                s = s.reshape(-1)
-                counts[r, n] = s.size
-                if s.size:
-                    pieces.append(s.astype(np.float64))      # float32 -> float64 is exact
-        times = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.float64)
+        times, counts = ingest.stack_spike_times(measurements)
         self.setMeasurementsFlat(times, counts)
 
     def setMeasurementsFlat(self, spike_times, spike_counts):
