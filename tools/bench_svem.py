@@ -36,6 +36,16 @@ def main():
     model = model_from_case(case, device=dev)
     kw = dict(max_iter=args.lbfgs_iters, lr=1.0, tolerance_grad=1e-7, tolerance_change=1e-9, line_search_fn="strong_wolfe")
     float(model.eval())                                   # warm-up: allocations, first launches
+    # torch.optim.LBFGS pulls in torch._dynamo / sympy on its first step (~3 s of imports): not part of svEM
+    x = torch.zeros(4, dtype=torch.float64, device=dev, requires_grad=True)
+    opt = torch.optim.LBFGS([x], max_iter=2, line_search_fn="strong_wolfe")
+
+    def _closure():
+        opt.zero_grad()
+        loss = ((x - 1.0) ** 2).sum()
+        loss.backward()
+        return loss
+    opt.step(_closure)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     hist, log = ecm_driver.maximize(model, em_max_iter=args.em_iters, lbfgs_kwargs=kw)
