@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, the final reductions, the whole-path orchestrators (device and host
 // buffers) and the host-side segment builder.  See include/svgpfa_b200.h.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -424,8 +425,8 @@ namespace {
 constexpr int HP_MAX_BLOCKS = 16;
 struct HostPipe {
     bool init = false;
-    cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t start = nullptr, drained = nullptr, copied[HP_MAX_BLOCKS], done[HP_MAX_BLOCKS];
+    cudaStream_t in = nullptr, out = nullptr, comp2 = nullptr;
+    cudaEvent_t start = nullptr, drained = nullptr, comp2_done = nullptr, copied[HP_MAX_BLOCKS], done[HP_MAX_BLOCKS];
 };
 thread_local HostPipe g_pipes[16];
 
@@ -437,6 +438,8 @@ HostPipe* host_pipe() {
     if (!p.init) {
         if (cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&p.comp2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&p.comp2_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&p.drained, cudaEventDisableTiming);
         for (int i = 0; i < HP_MAX_BLOCKS; ++i) {
@@ -491,6 +494,13 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
         cudaEventRecord(hp->start, st);            // earlier work on the caller's stream may still read the buffers
         cudaStreamWaitEvent(s_in, hp->start, 0);
     }
+    // Odd blocks run their kernels on a second compute stream, so that the tail wave of one block's kernels overlaps
+    // the next block's (20000 trials: 274.0 -> 269.6 ms, 2500 trials: 36.3 -> 35.4 ms; SVGPFA_HOST_STREAMS=1 switches
+    // it off).  Both streams accumulate into `shared` with atomics; per-trial outputs never overlap.
+    static int two_streams = -1;
+    if (two_streams < 0) { const char* e = getenv("SVGPFA_HOST_STREAMS"); two_streams = (e && atoi(e) == 1) ? 0 : 1; }
+    const bool two = hp && two_streams;
+    if (two) cudaStreamWaitEvent(hp->comp2, hp->start, 0);
     auto r_of = [&](int b) { return (size_t)(R * (size_t)b / (size_t)nb); };
     // K-major arrays: the block's trials are K separate runs, one per latent; with a uniform M they form a 2-D copy
     bool uniform = true;
@@ -542,13 +552,14 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
         svgpfa_dims db = *dims;
         db.r0 = (int32_t)r0;
         db.rn = nb > 1 ? (int32_t)n : 0;
-        if (hp) cudaStreamWaitEvent(st, hp->copied[b], 0);
+        cudaStream_t sc = (two && (b & 1)) ? hp->comp2 : st;
+        if (hp) cudaStreamWaitEvent(sc, hp->copied[b], 0);
         if (n > 0) {
-            rc = run_trial_stages(&db, dev, flags_run, false, st, nb == 1);
+            rc = run_trial_stages(&db, dev, flags_run, false, sc, nb == 1);
             if (rc) return rc;
         }
         if (hp) {
-            cudaEventRecord(hp->done[b], st);
+            cudaEventRecord(hp->done[b], sc);
             cudaStreamWaitEvent(s_out, hp->done[b], 0);
         }
         if (nb > 1) {                              // this block's per-trial gradients
@@ -560,6 +571,10 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
         }
     }
 #undef KM
+    if (two) {
+        cudaEventRecord(hp->comp2_done, hp->comp2);
+        cudaStreamWaitEvent(st, hp->comp2_done, 0);
+    }
     rc = svgpfa_finalize(dims, dev, flags_run, stream);
     if (nb == 1) stage_mark(1 + SVGPFA_STAGE_FINALIZE, st);
     if (rc) return rc;
