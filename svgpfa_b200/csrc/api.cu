@@ -376,6 +376,8 @@ extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* b
     const uint32_t kz = SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
     const bool reuse_spike = (flags & SVGPFA_REUSE_SPIKE) && !(flags & (kz | SVGPFA_GRAD_EMBEDDING));
     zero_accumulators(dims, buf, flags, reuse_spike, st);
+    // (Trial blocks alternating between two streams were measured here too: 263.2 vs 264.3 ms at config #5 -- the
+    //  kernels of one evaluation already fill the machine; only the pipelined host-buffer entry gains from it.)
     rc = run_trial_stages(dims, buf, flags, reuse_spike, st, true);
     if (rc) return rc;
     rc = svgpfa_finalize(dims, buf, flags, stream);
