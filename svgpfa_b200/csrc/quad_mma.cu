@@ -61,11 +61,26 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     {
         const size_t mo = (size_t)r * dm.MM + ds.mmoff;
-        for (int idx = tid; idx < MP * MP; idx += blockDim.x) {
-            const int i = idx / MP, j = idx - i * MP;
-            const bool in = (i < M) && (j < M);
-            Lis[i * LD + j] = in ? bf.Li[mo + (size_t)i * M + j] : 0.0;
-            Xs[i * LD + j] = in ? bf.X[mo + (size_t)i * M + j] : 0.0;
+        // Li and X are first needed by the V product, after the kernel evaluations of the first pass: when the rows
+        // are whole 16-byte chunks (M = MP, even offset) they are fetched with cp.async and awaited there, so the
+        // 16 KB of loads run under ~1400 cycles of arithmetic (ncu: the staging was 12-15 % long-scoreboard stalls)
+        if (M == MP && (mo & 1) == 0) {
+            const unsigned lis_s = (unsigned)__cvta_generic_to_shared(Lis), xs_s = (unsigned)__cvta_generic_to_shared(Xs);
+            for (int c = tid; c < MP * (MP / 2); c += blockDim.x) {
+                const int i = c / (MP / 2), jj = c - i * (MP / 2);
+                const size_t go = mo + (size_t)i * M + 2 * jj;
+                const unsigned so = (unsigned)(i * LD + 2 * jj) * 8u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lis_s + so), "l"(bf.Li + go) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_s + so), "l"(bf.X + go) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            for (int idx = tid; idx < MP * MP; idx += blockDim.x) {
+                const int i = idx / MP, j = idx - i * MP;
+                const bool in = (i < M) && (j < M);
+                Lis[i * LD + j] = in ? bf.Li[mo + (size_t)i * M + j] : 0.0;
+                Xs[i * LD + j] = in ? bf.X[mo + (size_t)i * M + j] : 0.0;
+            }
         }
         const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
         const size_t vo = (size_t)r * dm.KM + ds.moff;
@@ -84,23 +99,19 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
     const int ntq = (dm.Q + 31) / 32;
+    bool first_pass = true;                       // every warp has at least one pass (nw <= ntq)
     for (int qt0 = warp; qt0 < ntq; qt0 += nw) {
         const int qbase = qt0 * 32;
         const int q_lane = qbase + lane;
         const bool valid = q_lane < dm.Q;
         const double t_lane = valid ? bf.tq[(size_t)r * dm.Q + q_lane] : 0.0;
         tt[lane] = t_lane;
-        if (BWD) {
-            double mbar = 0.0, vbar = 0.0;
-            if (valid) {
-                const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;
-                for (int p = 0; p < dm.n_ntiles; ++p) {
-                    mbar += bf.mubar_part[p * part_stride + o];
-                    vbar += bf.varbar_part[p * part_stride + o];
-                }
+        if (BWD && valid) {                          // the partial sums are read after the kernel evaluations (below):
+            const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;      // pull them into L1 meanwhile
+            for (int p = 0; p < dm.n_ntiles; ++p) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(bf.mubar_part + p * part_stride + o));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(bf.varbar_part + p * part_stride + o));
             }
-            mbs[lane] = mbar;
-            vbs[lane] = vbar;
         }
         // ---- kernel values.  BWD: lane <-> point, K[j][q] -> tileU (rolled loop; the tile feeds abar and the V
         //      product).  FWD: directly in B-fragment registers kf[ks][qt] = kappa(t[8 qt + g] - z[4 ks + tg]) --
@@ -111,6 +122,16 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
 #pragma unroll 2
             for (int j = 0; j < MP; ++j)
                 tileU[j * LDT + lane] = (valid && j < M) ? kappa_val_t(kc, t_lane - zs[j], etab) : 0.0;
+            double mbar = 0.0, vbar = 0.0;
+            if (valid) {
+                const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;
+                for (int p = 0; p < dm.n_ntiles; ++p) {
+                    mbar += bf.mubar_part[p * part_stride + o];
+                    vbar += bf.varbar_part[p * part_stride + o];
+                }
+            }
+            mbs[lane] = mbar;
+            vbs[lane] = vbar;
         } else {
             __syncwarp();                                            // tt visible
             double t4[4];
@@ -138,6 +159,11 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                 s_ = fma(mbs[q], tileU[lane * LDT + q], s_);
             }
             ab_own += s_;
+        }
+        if (first_pass) {                         // Li, X of the cp.async staging become visible to the whole CTA
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            first_pass = false;
         }
         // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]
         double v[MT][4][2];
