@@ -244,6 +244,66 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_fwd_kernel(svgpfa_dims d
 }
 
 // ------------------------------------------------------------------------------------------
+// M <= 32: the same work with one WARP per (trial, latent), like kzz_chol_warp_kernel: Li staged in shared memory
+// (coalesced), lane j owns column j of Ls in registers, X[i][j] = sum_p Li[i][p] Ls[p][j] with the entries of Li read
+// as warp-uniform (broadcast) loads and row i of X written straight from the registers (one coalesced store per row);
+// c = Li m with lane = row, alpha = Li^T c with lane = column.  No block barriers.
+__global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpfa_dims dm, svgpfa_buffers bf, int nprob) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prob = blockIdx.x * KC_WARPS + warp;
+    if (prob >= nprob) return;                        // whole warps leave; there is no block barrier below
+    const int rl = prob / dm.K, k = prob - rl * dm.K, r = dm.r0 + rl;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const int M = ds.M;
+    double* A = sm + (size_t)warp * KC_WSM;           // Li, rows / columns >= M zero
+    double* vec = A + 32 * KC_LD;                     // m, then c
+    const size_t mo = (size_t)r * dm.MM + ds.mmoff, vo = (size_t)r * dm.KM + ds.moff;
+    const double* Lig = bf.Li + mo;
+    for (int i = 0; i < 32; ++i) A[i * KC_LD + lane] = (i < M && lane < M) ? Lig[(size_t)i * M + lane] : 0.0;
+    vec[lane] = lane < M ? bf.m[(size_t)dm.R * ds.moff + (size_t)r * M + lane] : 0.0;
+    const double* cvec = bf.cholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
+    double ls[32];                                    // column `lane` of Ls (row-major tril vector, miscUtils.py:135-139)
+#pragma unroll
+    for (int p = 0; p < 32; ++p) ls[p] = (p < M && lane <= p) ? cvec[p * (p + 1) / 2 + lane] : 0.0;
+    const double ldiag = lane < M ? cvec[lane * (lane + 1) / 2 + lane] : 1.0;
+    __syncwarp();
+    double part = 0.0;
+    double* Xg = bf.X + mo;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int p = 0; p <= i; ++p) {
+            const double l = A[i * KC_LD + p];
+            if ((p & 3) == 0) s0 = fma(l, ls[p], s0);
+            else if ((p & 3) == 1) s1 = fma(l, ls[p], s1);
+            else if ((p & 3) == 2) s2 = fma(l, ls[p], s2);
+            else s3 = fma(l, ls[p], s3);
+        }
+        const double x = (s0 + s1) + (s2 + s3);       // 0 above the diagonal by itself (ls[p] = 0 for p < lane)
+        if (i < M && lane < M) Xg[(size_t)i * M + lane] = x;
+        part = fma(x, x, part);
+    }
+    double c = 0.0;                                   // c = Li m, lane = row (Li is stored with zeros above the diagonal)
+#pragma unroll 8
+    for (int p = 0; p < 32; ++p) c = fma(A[lane * KC_LD + p], vec[p], c);
+    part += c * c - 2.0 * log(fabs(ldiag));
+    __syncwarp();
+    vec[lane] = c;
+    __syncwarp();
+    double al = 0.0;                                  // alpha = Li^T c, lane = column
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) al = fma(A[i * KC_LD + lane], vec[i], al);
+    if (lane < M) {
+        bf.alpha[vo + lane] = al;
+        bf.c[vo + lane] = c;
+    }
+    const double tot = warp_sum(part);
+    if (lane == 0) bf.kl_rk[(size_t)r * dm.K + k] = 0.5 * (tot + 2.0 * bf.logdetL[(size_t)r * dm.K + k] - (double)M);
+}
+
+// ------------------------------------------------------------------------------------------
 // C(i,j) = sum_{p in [lo,hi]} a(i,p) b(p,j) on the FP64 tensor path: 8x8 output tiles, one warp per tile,
 // k-steps of 4 (mma.sync.m8n8k4.f64: 256 FMAs for one issue slot and two operand loads).  The matrices are
 // stored full with explicit zeros outside their triangle and zero padding up to MP (multiple of 8), so a tile may
@@ -469,9 +529,17 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
 extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "indpoints_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    const size_t smem = ip_smem(dims->Mmax, 2, 2);
-    cudaFuncSetAttribute(indpoints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    indpoints_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    static int variant = -1;                        // SVGPFA_IPFWD_VARIANT=1: the CTA-per-matrix kernel also for M <= 32
+    if (variant < 0) { const char* e = getenv("SVGPFA_IPFWD_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (dims->Mmax <= 32 && variant != 1) {
+        const int nprob = svgpfa_ntrials(dims) * dims->K;
+        const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
+        indpoints_fwd_warp_kernel<<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
+    } else {
+        const size_t smem = ip_smem(dims->Mmax, 2, 2);
+        cudaFuncSetAttribute(indpoints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        indpoints_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
+    }
     SVGPFA_CHECK_LAUNCH("indpoints_fwd");
     return SVGPFA_OK;
 }
