@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(IP_BWD_THREADS) indpoints_bwd_kernel(svgpfa_di
 
 int ip_bwd_threads() {          // SVGPFA_IPBWD_THREADS (experiments): 128 or 256
     static int t = 0;
-    if (!t) { const char* e = getenv("SVGPFA_IPBWD_THREADS"); t = e ? atoi(e) : IP_BWD_THREADS; if (t != 128 && t != 256) t = IP_BWD_THREADS; }
+    if (!t) { const char* e = getenv("SVGPFA_IPBWD_THREADS"); t = e ? atoi(e) : IP_BWD_THREADS; if (t != 32 && t != 64 && t != 128 && t != 256) t = IP_BWD_THREADS; }
     return t;
 }
 
