@@ -16,8 +16,14 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                 kernel's mean device time inside the timed region (CUDA events recorded by the library);
                 peak = DFMA throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry).
   stages_ms     mean device time of every kernel stage inside the timed region
-  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample of the same workload
+  cpu_baseline  the oracle port timed on this box's host cores on a bounded sample of the same workload, with the
+                parity of EVERY gradient group of the timed configuration on that sample
   e2e           same metric through the host-buffer C-ABI entry, copies inside the timed region
+  elbo, shared_checksum   the bound and a checksum of the all-reduced [elbo | dC | dd | dtheta] buffer of the last
+                timed step: the synthetic trials are seeded per trial block, so an N-rank run evaluates exactly the
+                data of the 1-rank run and these must agree across N (to rounding)
+  closures      secondary figures of SURVEY.md §8d: E-step closure (m, cholVecs gradients only) and embedding-M-step
+                closure (cached statistics) evaluations per second
 """
 from __future__ import annotations
 
@@ -69,6 +75,7 @@ def config_dict(args, cfg, world):
                         f"{', heavy ragged spikes' if cfg['ragged'] else ''}, reg=1e-3",
             "unit_of_work": "buildKernelsMatrices(); eval(); backward() over all parameter groups",
             "trials_total": cfg["R"], "trials_per_gpu": -(-cfg["R"] // world), "parallelism": f"trial-shard x{world}",
+            "sharding": "contiguous trial blocks balanced by estimated cost (spikes x pairs + per-trial quadrature work)",
             "l2": "inputs larger than L2 (spike times + per-trial parameters re-read every step)",
             "reduced": args.trials is not None}
 
@@ -190,9 +197,9 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def measure_peaks(device):
-    """DFMA / libdevice exp / sincospi / library exp throughput of this GPU (per second)."""
+    """DFMA / libdevice exp / sincospi / library exp throughput of this GPU (per second); probes library."""
     from svgpfa_b200 import _cabi
-    lib = _cabi.lib()
+    lib = _cabi.probes()
     nsm = torch.cuda.get_device_properties(device).multi_processor_count
     blocks = nsm * 8
     out = torch.empty(blocks * 256, dtype=torch.float64, device=device)
@@ -203,7 +210,7 @@ def measure_peaks(device):
         for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _cabi.check(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), stream))
+            _cabi.check_probe(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), stream))
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1)
@@ -248,10 +255,13 @@ def run_b200(args):
         pg = dist.group.WORLD
     cfg = workload(args)
     R = cfg["R"]
-    # contiguous trial blocks; the synthetic generator draws every trial from the same distribution, so the
-    # expected cost per trial is uniform (measured spike counts would be used for real data)
+    # contiguous trial blocks balanced by estimated cost (spikes x pairs + per-trial quadrature work); every rank
+    # derives the same cuts from the spike counts of ALL trials (cheap: counts only), then generates its own shard
     from svgpfa_b200 import sharding
-    r0, r1 = sharding.trial_blocks(np.ones(R), world)[rank]
+    per_trial_spikes = synthetic.spike_counts_torch(cfg, device, seed=0).sum(1).cpu().numpy()
+    costs = sharding.trial_costs(per_trial_spikes, cfg["N"], cfg["K"], cfg["M"], cfg["Q"])
+    blocks = sharding.trial_blocks(costs, world)
+    r0, r1 = blocks[rank]
     case = synthetic.make_case_torch(cfg, device, seed=0, r0=r0, r1=r1)
     S_local = int(case["spike_times"].numel())
     model = model_from_case(case, device=device, process_group=pg)
@@ -274,7 +284,7 @@ def run_b200(args):
 
     for _ in range(max(3, args.warmup)):
         v = step()
-    elbo = float(v.item())
+    model.checkErrors()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -291,13 +301,19 @@ def run_b200(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     start.record()
-    for i in range(args.steps):
-        lib.svgpfa_set_stage_events(ev_arr[i])
-        step()
+    for i in range(args.steps):          # no host synchronisation inside: the error state of every evaluation comes
+        lib.svgpfa_set_stage_events(ev_arr[i])          # back through the model's asynchronous header copy
+        v = step()
     lib.svgpfa_set_stage_events(None)
     stop.record()
     barrier()
     wall1 = time.time()
+    model.checkErrors()
+    elbo = float(v.item())
+    last_shared = model._last_shared.detach()
+    checksum = {"sum": float(last_shared[8:].sum().item()), "l2": float(last_shared[8:].norm().item()),
+                "dC_l2": float(last_shared[8:8 + cfg["N"] * cfg["K"]].norm().item()),
+                "dtheta_l2": float(last_shared[8 + cfg["N"] * cfg["K"] + cfg["N"]:].norm().item())}
     ms_total = start.elapsed_time(stop)
     stage_ms = np.zeros(len(_cabi.STAGES))
     for row in evs:
@@ -317,6 +333,50 @@ def run_b200(args):
     if rank == 0:
         sampler.stop()
 
+    # ---- secondary figures: the closures svEM's E-step and embedding M-step evaluate
+    def time_closure(fn, n):
+        for _ in range(2):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def closure_of(params, objective):
+        def fn():
+            for p in params:
+                p.grad = None
+            cur = -objective()
+            cur.backward()
+        return fn
+
+    n_sec = max(2, min(args.steps, 5))
+    set_requires_grad(model, posterior=True, embedding=False, kernels=False, indlocs=False)
+    mode0 = model.shard_mode
+    ms_estep = time_closure(closure_of(model.getSVPosteriorOnIndPointsParams(), model.eval), n_sec)     # rank-local
+    set_requires_grad(model, posterior=False, embedding=True, kernels=False, indlocs=False)
+    stats = model.computeSVPosteriorOnLatentsStats()
+    ms_emb = time_closure(closure_of(model.getSVEmbeddingParams(),
+                                     lambda: model.evalELLSumAcrossTrialsAndNeurons(svPosteriorOnLatentsStats=stats)), n_sec)
+    del stats
+    model._cached_keepalive = None
+    model.shard_mode = mode0
+    set_requires_grad(model)
+    model.checkErrors()
+    closures = {"estep_closure": {"ms": ms_estep, "evals_per_sec": 1e3 / ms_estep,
+                                  "what": "eval + backward w.r.t. m, cholVecs only (svEM.py:218-223); the spike term is "
+                                          "served from its cached statistic (Z, theta, C unchanged); rank-local under sharding"},
+                "mstep_embedding_closure": {"ms": ms_emb, "evals_per_sec": 1e3 / ms_emb,
+                                            "what": "ELL from cached latent statistics + backward w.r.t. C, d "
+                                                    "(svEM.py:225-232): quadrature embedding kernel + HBM-bound spike gather"}}
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -329,11 +389,7 @@ def run_b200(args):
         e_start.record()
         n_e2e = max(2, min(args.steps, 5))
         for _ in range(n_e2e):
-            elbo_h, h2d, d2h = model.evalAndGradHost(io, copy_static=True)
-            if world > 1:
-                sh = io["shared"].to(device, non_blocking=True)
-                dist.all_reduce(sh)
-                io["shared"].copy_(sh)
+            elbo_h, h2d, d2h = model.evalAndGradHost(io, copy_static=True)      # all-reduces on the device when sharded
         e_stop.record()
         barrier()
         ms_e2e = e_start.elapsed_time(e_stop) / n_e2e
@@ -450,20 +506,30 @@ def run_b200(args):
         cpu = {"value": 1.0 / full, "unit": UNIT, "cores": threads, "kind": "port", "cpu": cpu_model_name(),
                "sample": f"first {r_sub} of {R} trials, best of 2 evaluations, time extrapolated linearly to {R} trials",
                "measured_s_on_sample": dt}
-        # parity of the timed configuration on that sample (same inputs, GPU path vs oracle)
+        # parity of the timed configuration on that sample (same inputs, GPU path vs oracle): the bound and EVERY
+        # gradient group, worst relative error (||delta||_2 / ||ref||_2) per group
+        from svgpfa_b200.testing import grads_as_dict
         sub = model_from_case(synthetic.case_to_numpy(case, 0, r_sub), device=device)
         set_requires_grad(sub)
         vs = sub.eval()
         vs.backward()
         cpu["parity_elbo_rel_err"] = abs(vs.item() - ref["elbo"]) / abs(ref["elbo"])
-        gC = sub.getSVEmbeddingParams()[0].grad.cpu().numpy()
-        cpu["parity_gradC_rel_err"] = float(np.linalg.norm(gC - ref["grad_C"]) / np.linalg.norm(ref["grad_C"]))
+        got = grads_as_dict(sub)
+        worst = {}
+        for key, g in got.items():
+            grp = key.rsplit("_", 1)[0] if key[-1].isdigit() else key
+            e = float(np.linalg.norm(g.reshape(-1) - ref[key].reshape(-1)) / np.linalg.norm(ref[key].reshape(-1)))
+            worst[grp] = max(worst.get(grp, 0.0), e)
+        cpu["parity_grad_rel_err"] = worst
+        cpu["parity_ok"] = bool(cpu["parity_elbo_rel_err"] <= 1e-10 and max(worst.values()) <= 1e-8)
+        del sub
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "b200",
-            "config": config_dict(args, cfg, world), "elbo": elbo, "spikes_total": int(tot_S.item()),
-            "clocks": clocks, "gpu_launches": 9 * args.steps,
+            "config": config_dict(args, cfg, world), "elbo": elbo, "shared_checksum": checksum,
+            "spikes_total": int(tot_S.item()), "trial_blocks": [list(b) for b in blocks],
+            "clocks": clocks, "gpu_launches": 10 * args.steps, "closures": closures,
             "stages_ms": {n: float(x) for n, x in zip(_cabi.STAGES, st.tolist())},
             "roofline": roofline, "peaks_measured": {k: float(v) for k, v in peaks.items()}}
     if e2e is not None:

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 2
+#define SVGPFA_ABI_VERSION 3
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -83,6 +83,9 @@ typedef struct svgpfa_dims {
     int32_t r0, rn;               /* trial range [r0, r0 + rn) the per-trial stages work on; rn = 0: all R trials.
                                      Sizes, strides and layouts are always those of the full shard (R); the host-buffer
                                      entry uses the range to pipeline copies and kernels over blocks of trials. */
+    int32_t spike_chunks;         /* tuning: neuron ranges per trial in the spike kernel's grid; 0 = automatic
+                                     (tests force 1: whole-trial ranges, several spike tiles per CTA) */
+    int32_t reserved0;
 } svgpfa_dims;
 
 #define SVGPFA_NTRIALS(d) ((d)->rn ? (d)->rn : (d)->R)
@@ -123,11 +126,15 @@ typedef struct svgpfa_buffers {
     double* mubar_part;          /* n_ntiles*R*K*Q  [tile][r][k][q] per-neuron-tile partials of dELBO/dmu_q */
     double* varbar_part;         /* n_ntiles*R*K*Q  same layout                                  */
     double* term1_part;          /* SVGPFA_TERM1_SLOTS partial sums of the intensity integral  */
+    double* fin_part;            /* 3*SVGPFA_FIN_SLOTS per-block partials of svgpfa_finalize (KL, term1, term2), summed in
+                                    fixed order: the bound is run-to-run reproducible given its inputs */
     /* ---- cached-statistics path (embedding M-step) -------------------------------------- */
     double* mu_s;                /* S*K   latent means at spike times, [s][k]                   */
     /* ---- outputs ------------------------------------------------------------------------ */
-    double* shared;              /* SVGPFA_SHARED_HDR + N*K + N + TH: [elbo, ell, kl, term1, term2, 0,0,0 | dC | dd | dtheta]
-                                    -- the buffer a multi-GPU caller all-reduces */
+    double* shared;              /* SVGPFA_SHARED_HDR + N*K + N + TH: [elbo, ell, kl, term1, term2, status, r, k | dC | dd | dtheta]
+                                    -- the buffer a multi-GPU caller all-reduces; status/r/k = info[0..2]
+                                    as doubles, so that the sum over shards is > 0 iff some shard's Kzz failed and one
+                                    small device->host copy of the header carries the bound AND the error state */
     double* gZ;                  /* R*KM  K-major */
     double* gm;                  /* R*KM  K-major */
     double* gcholvec;            /* R*PP  K-major */
@@ -136,6 +143,7 @@ typedef struct svgpfa_buffers {
 
 #define SVGPFA_SHARED_HDR 8
 #define SVGPFA_TERM1_SLOTS 4096
+#define SVGPFA_FIN_SLOTS 1024
 
 int svgpfa_abi_version(void);
 const char* svgpfa_last_error(void);
@@ -222,26 +230,21 @@ typedef struct svgpfa_host_io {
 int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                           uint32_t flags, void* stream);
 
-/* Measurement hooks (bench.py only).
+/* Destroys the side streams and events svgpfa_elbo_grad_host created for the CALLING host thread (one set per device,
+ * created on first use); the thread must have drained its streams.  Optional: a process that exits need not call it. */
+int svgpfa_release_thread_resources(void);
+
+/* Measurement hook (bench.py only).
  * svgpfa_set_stage_events: when `events` is non-NULL the next svgpfa_elbo_grad calls on this host thread
  *   record events[0] before the first stage and events[i+1] after stage i (stages in the order of
  *   SVGPFA_STAGE_*; a skipped stage records its event immediately), so that a caller can read every
  *   kernel's device time inside its own timed region.  `events` = SVGPFA_N_STAGES+1 cudaEvent_t handles.
  *   Pass NULL to switch recording off.
- * svgpfa_peak_probe: FP64 pipe micro-benchmarks used as roofline denominators (SURVEY.md §8d asks the
- *   builder to MEASURE pi_fma / pi_exp / pi_sin).  kind 0: dependent-chain-free DFMA, 1: libdevice exp,
- *   2: libdevice sincospi, 3: this library's exp (svgpfa_exp_neg), 4: mma.m8n8k4.f64 (8 per thread-iteration,
- *   32 FMAs per thread each).  Launches `blocks` x 256 threads, each
- *   doing `iters` x 8 operations; the caller times it with events.  out: `blocks*256` doubles (sink). */
+ * (The FP64 peak probes and the exp test hooks live in a separate library: include/svgpfa_b200_probes.h.) */
 enum { SVGPFA_STAGE_KZZ_CHOL = 0, SVGPFA_STAGE_INDPOINTS_FWD, SVGPFA_STAGE_QUAD_LATENT_FWD, SVGPFA_STAGE_QUAD_EMBED,
        SVGPFA_STAGE_QUAD_LATENT_BWD, SVGPFA_STAGE_SPIKE, SVGPFA_STAGE_INDPOINTS_BWD, SVGPFA_STAGE_FINALIZE,
        SVGPFA_N_STAGES };
 int svgpfa_set_stage_events(void** events);
-int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, void* stream);
-/* Test hook: y_fast[i] = the library's exp for non-positive arguments, y_ref[i] = libdevice exp(x[i]). */
-int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream);
-/* Test hook: y[i] = 2^(-min(w2[i], 2.61e5) / 256), the pre-scaled exponential of the spike kernel (w2 >= 0). */
-int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

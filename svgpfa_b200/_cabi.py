@@ -9,13 +9,16 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("SVGPFA_LIB") or os.path.join(PKG, "libsvgpfa_b200.so")   # SVGPFA_LIB: experiments only
+LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
+PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
 TERM1_SLOTS = 4096
+FIN_SLOTS = 1024
+SHARED_STATUS = 5            # shared[5..7] = (status, trial, latent) of a failed Cholesky, as doubles
 KERNEL_EXPQUAD, KERNEL_PERIODIC = 0, 1
 GRAD_POSTERIOR, GRAD_EMBEDDING, GRAD_KERNEL, GRAD_INDLOCS = 1, 2, 4, 8
 GRAD_ALL = 15
@@ -29,13 +32,14 @@ class LatentDesc(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("R", "N", "K", "Q", "KM", "MM", "PP", "TH", "Mmax", "n_ntiles")] + [
-        ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc)), ("r0", C.c_int32), ("rn", C.c_int32)]
+        ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc)), ("r0", C.c_int32), ("rn", C.c_int32),
+        ("spike_chunks", C.c_int32), ("reserved0", C.c_int32)]
 
 
 BUFFER_FIELDS = (
     "desc", "kscale", "theta", "Z", "m", "cholvec", "C", "d", "tq", "wq", "spike_t", "seg_off", "spike_cnt",
     "L", "Li", "X", "c", "alpha", "logdetL", "kl_rk", "A_q", "abar_q", "abar_spk", "dz_acc", "dth_part",
-    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "mu_s",
+    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "mu_s",
     "shared", "gZ", "gm", "gcholvec", "info")
 
 
@@ -71,6 +75,11 @@ SYMBOLS = {
     "svgpfa_build_segments_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgpfa_elbo_grad_host": (C.c_int, [_P(Dims), _P(Buffers), _P(HostIO), C.c_uint32, C.c_void_p]),
     "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),
+    "svgpfa_release_thread_resources": (C.c_int, []),
+}
+# include/svgpfa_b200_probes.h (separate library)
+PROBE_SYMBOLS = {
+    "svgpfa_probes_last_error": (C.c_char_p, []),
     "svgpfa_peak_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "svgpfa_exp_neg_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "svgpfa_exp2m_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -98,6 +107,29 @@ def lib():
             raise RuntimeError("libsvgpfa_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
+
+
+_probes = None
+
+
+def probes():
+    """The probes / test-hooks library (bench.py roofline leg, tools/, tests/ only)."""
+    global _probes
+    if _probes is None:
+        if not os.path.exists(PROBES_LIB_PATH):
+            raise RuntimeError(f"{PROBES_LIB_PATH} not found (run `python -m svgpfa_b200.build`)")
+        handle = C.CDLL(PROBES_LIB_PATH)
+        for name, (res, args) in PROBE_SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probes = handle
+    return _probes
+
+
+def check_probe(rc: int, what: str = ""):
+    if rc != 0:
+        raise RuntimeError(f"probe call failed ({rc}) {what}: {probes().svgpfa_probes_last_error().decode()}")
 
 
 def check(rc: int, what: str = ""):

@@ -20,6 +20,9 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libsvgpfa_b200.so")
 SOURCES = ["api.cu", "indpoints.cu", "quad.cu", "quad_mma.cu", "spike.cu"]
+# measurement probes and test hooks: a separate library, never loaded by the product path
+PROBES_LIB = os.path.join(PKG, "libsvgpfa_b200_probes.so")
+PROBES_SOURCES = ["probes.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
@@ -44,6 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "svgpfa_b200.h"))
+    headers.append(os.path.join(INCLUDE, "svgpfa_b200_probes.h"))
     headers.append(os.path.abspath(__file__))
 
     def compile_one(src):
@@ -60,14 +64,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(res.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-cudart", "static", "-Xcompiler", "-fPIC"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with ThreadPoolExecutor(max_workers=len(SOURCES) + len(PROBES_SOURCES)) as ex:
+        all_objs = list(ex.map(compile_one, SOURCES + PROBES_SOURCES))
+    for lib, objs in ((LIB, all_objs[:len(SOURCES)]), (PROBES_LIB, all_objs[len(SOURCES):])):
+        if force or _stale(lib, objs):
+            cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                          "-cudart", "static", "-Xcompiler", "-fPIC"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB
 
 

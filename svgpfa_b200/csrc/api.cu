@@ -18,181 +18,14 @@ inline void stage_mark(int idx, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// FP64 pipe probes
-// ------------------------------------------------------------------------------------------
-// Are DFMA (FP64 pipe) and mma.m8n8k4.f64 (tensor DMMA sub-pipe) independent?  MIX = 8 DFMA + NM DMMA per iteration.
-template <int NF, int NM>
-__global__ void __launch_bounds__(256) mix_probe_kernel(long iters, double* out) {
-    const double av = 1.0 + 1e-9 * threadIdx.x, bv = 1.0 - 1e-9 * threadIdx.x;
-    double c[8][2], a[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { c[e][0] = c[e][1] = 1e-3 * e; a[e] = 1e-3 * (threadIdx.x + 1) + 0.01 * e; }
-    const double m = 0.999999, k = 1e-9;
-    for (long i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (e < NM)
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(c[e][0]), "+d"(c[e][1]) : "d"(av), "d"(bv));
-            if (e < NF) a[e] = fma(a[e], m, k);
-        }
-    }
-    double s = 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s += c[e][0] + c[e][1] + a[e];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// Issue-model probes: 8 independent FP64 chains per thread with ALL operands in distinct registers (the DFMA probe
-// above has two constant operands), optionally interleaved with NI integer instructions or one shared-memory load
-// per FP64 instruction.  OP: 0 = DFMA (3 register operands), 1 = DADD, 2 = DMUL.
-template <int OP, int NI, int LDS>
-__global__ void __launch_bounds__(256) issue_probe_kernel(long iters, double* out) {
-    __shared__ double sm[256];
-    sm[threadIdx.x] = 1e-9 * threadIdx.x;
-    __syncthreads();
-    double a[8], b[8], c[8];
-    int k[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        a[e] = out[(threadIdx.x + e) & 255] * 1e-300 + 1e-3 * (threadIdx.x + 1) + 0.01 * e;
-        b[e] = 0.999999 - 1e-9 * e + out[(threadIdx.x + 8 + e) & 255] * 1e-300;
-        c[e] = 1e-9 * (e + 1) + out[(threadIdx.x + 16 + e) & 255] * 1e-300;
-        k[e] = threadIdx.x + e;
-    }
-    for (long i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (OP == 0) a[e] = fma(a[e], b[e], c[e]);
-            else if (OP == 1) a[e] = a[e] + c[e];
-            else a[e] = a[e] * b[e];
-            if (NI >= 1) k[e] = k[e] * 3 + 1;
-            if (NI >= 2) k[e] = (k[e] >> 3) ^ k[e];
-            if (NI >= 3) k[e] = k[e] * 5 + 7;
-            if (LDS) c[e] += sm[(k[e] + (int)i) & 255] * 0.0;   // 1 LDS (+1 DFMA) per step
-        }
-    }
-    double s = 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s += a[e] + (double)k[e] + c[e];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// The spike kernel's evaluation sequence in isolation (no segments, no staging): per step 4 evaluations of
-// w = t sc + zs, kappa = 2^(-w^2/256), pn += kappa, p1 += kappa w, p2 += kappa w^2 with t read from shared memory.
-// MODE 0: as in the kernel; 1: without the moment accumulations (KGRAD = false); 2: table entry replaced by a constant
-// (no table LDS); 3: without the spike-time LDS.
-template <int MODE>
-__global__ void __maxnreg__(128) eval_probe_kernel(long iters, double* out) {
-    __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
-    __shared__ double ts[1024];
-    svgpfa_load_exp2m_tab(tab);
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) ts[i] = 1e-3 * i;
-    __syncthreads();
-    const unsigned lane_tab = svgpfa_exp2m_lane_tab(tab);
-    const double sc = 13.0 + out[threadIdx.x] * 1e-300, zs = -0.37 * (threadIdx.x & 31) - 1e-3 * (threadIdx.x >> 5);
-    double pn = 0.0, p1 = 0.0, p2 = 0.0;
-    for (long i = 0; i < iters; ++i) {
-        const double* tp = ts + ((i * 4) & 1020);
-        double t[4], w[4], w2[4], kv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) t[e] = MODE == 3 ? 1e-3 * e + pn * 1e-300 : tp[e];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { w[e] = fma(t[e], sc, zs); w2[e] = w[e] * w[e]; }
-        if (MODE == 2) {
-            const double MAGIC = 6755399441055744.0, L = SVGPFA_EXP2M_L;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double tt = MAGIC - w2[e];
-                const double u = w2[e] + (tt - MAGIC);
-                const int n = __double2loint(tt);
-                double q = fma(u, L * L * L * L / 24.0, -L * L * L / 6.0);
-                q = fma(u, q, L * L / 2.0);
-                q = fma(-u, q, L);
-                const double T = __hiloint2double(0x3ff00000 + (n << 12), n & 255);
-                kv[e] = fma(-(T * u), q, T);
-            }
-        } else {
-            svgpfa_exp2m_n<4>(w2, lane_tab, kv);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            pn += kv[e];
-            if (MODE != 1) { p1 = fma(kv[e], w[e], p1); p2 = fma(kv[e], w2[e], p2); }
-        }
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = pn + p1 + p2;
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(256) peak_probe_kernel(long iters, double* out) {
-    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
-    svgpfa_load_exp_tab(etab);
-    __syncthreads();
-    const double seed = 1e-3 * (threadIdx.x + 1) + 1e-7 * blockIdx.x;
-    double a[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = seed + 0.01 * e;
-    const double m = 0.999999, c = 1e-9;
-    for (long i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (KIND == 0) a[e] = fma(a[e], m, c);
-            else if (KIND == 1) a[e] = exp(-a[e] * 0.5) + c;           // 1 mul + 1 add + exp
-            else if (KIND == 2) { double s, cs; sincospi(a[e], &s, &cs); a[e] = s * cs + 0.25; }
-            else a[e] = svgpfa_exp_neg(-a[e] * 0.5, etab) + c;
-        }
-    }
-    double s = 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s += a[e];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// FP64 tensor-core probe: 8 independent mma.m8n8k4.f64 accumulator chains per warp (256 FMAs per instruction).
-__global__ void __launch_bounds__(256) dmma_probe_kernel(long iters, double* out) {
-    const double av = 1.0 + 1e-9 * threadIdx.x, bv = 1.0 - 1e-9 * threadIdx.x;
-    double c[8][2];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) c[e][0] = c[e][1] = 1e-3 * e;
-    for (long i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(c[e][0]), "+d"(c[e][1]) : "d"(av), "d"(bv));
-    }
-    double s = 0.0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s += c[e][0] + c[e][1];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-__global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n) {
-    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
-    svgpfa_load_exp_tab(etab);
-    __syncthreads();
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        yf[i] = svgpfa_exp_neg(x[i], etab);
-        yr[i] = exp(x[i]);
-    }
-}
-
-__global__ void exp2m_eval_kernel(const double* w2, double* y, long n) {
-    __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
-    svgpfa_load_exp2m_tab(tab);
-    __syncthreads();
-    const unsigned lane_tab = svgpfa_exp2m_lane_tab(tab);
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        y[i] = svgpfa_exp2m(svgpfa_exp2m_clamp(w2[i]), lane_tab);
-}
-
-// ------------------------------------------------------------------------------------------
 // reductions into `shared`
 //   shared[2] = KL, shared[3] = term1, shared[4] += alpha . abar_spk + cnt . d, dtheta = sum_r dth_part,
 //   dd += spike counts
 // ------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 
+// Per-block partials go to fin_part[3][SVGPFA_FIN_SLOTS] and are summed in slot order by finalize_combine_kernel: no
+// floating-point atomics here, so the three scalars are reproducible run to run given the stage buffers.
 __global__ void __launch_bounds__(FIN_THREADS) finalize_reduce_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags,
                                                                       int use_abar) {
     __shared__ double red[32];
@@ -211,9 +44,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_reduce_kernel(svgpfa_dim
     const double st1 = block_sum(t1, red);
     const double st2 = block_sum(t2, red);
     if (threadIdx.x == 0) {
-        atomicAdd(bf.shared + 2, skl);
-        atomicAdd(bf.shared + 3, st1);
-        atomicAdd(bf.shared + 4, st2);
+        bf.fin_part[blockIdx.x] = skl;
+        bf.fin_part[SVGPFA_FIN_SLOTS + blockIdx.x] = st1;
+        bf.fin_part[2 * SVGPFA_FIN_SLOTS + blockIdx.x] = st2;
     }
     if (flags & SVGPFA_GRAD_KERNEL) {
         // dtheta[i] = sum_r dth_part[r][i]: one warp per parameter, lanes stride over trials
@@ -228,12 +61,44 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_reduce_kernel(svgpfa_dim
     }
 }
 
-__global__ void finalize_combine_kernel(svgpfa_buffers bf, int with_kl) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+// one warp: lane l sums slots l, l + 32, ... in order, then a fixed shuffle tree.  shared[4] may already hold the
+// C part of term2 (cached-statistics path: written by the gather kernel), hence "+=".
+__global__ void finalize_combine_kernel(svgpfa_buffers bf, int nslots, int with_kl) {
+    const int lane = threadIdx.x;
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        for (int i = lane; i < nslots; i += 32) s += bf.fin_part[c * SVGPFA_FIN_SLOTS + i];
+        v[c] = warp_sum(s);
+    }
+    if (lane == 0) {
         double* s = bf.shared;
+        s[2] = with_kl ? v[0] : 0.0;
+        s[3] = v[1];
+        s[4] += v[2];
         const double ell = -s[3] + s[4];
         s[1] = ell;
         s[0] = with_kl ? ell - s[2] : ell;
+        s[5] = (double)bf.info[0];
+        s[6] = (double)bf.info[1];
+        s[7] = (double)bf.info[2];
+    }
+}
+
+// every accumulator of one evaluation in ONE launch (was six memset nodes)
+struct ZeroList {
+    double* p[6];
+    size_t n[6];
+    int cnt;
+};
+
+__global__ void __launch_bounds__(256) zero_kernel(ZeroList zl) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gstr = (size_t)gridDim.x * blockDim.x;
+    for (int a = 0; a < zl.cnt; ++a) {
+        double* p = zl.p[a];
+        const size_t n = zl.n[a];
+        for (size_t i = gtid; i < n; i += gstr) p[i] = 0.0;
     }
 }
 
@@ -248,6 +113,19 @@ size_t shared_len(const svgpfa_dims* d) { return SVGPFA_SHARED_HDR + (size_t)d->
 
 }  // namespace
 
+int svgpfa_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev & 63].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 int svgpfa_set_error(int code, const char* where, cudaError_t ce) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, ce == cudaSuccess ? (code == SVGPFA_E_ARG ? "bad argument" : "unsupported") : cudaGetErrorString(ce));
     return code;
@@ -260,65 +138,25 @@ extern "C" int svgpfa_set_stage_events(void** events) {
     return SVGPFA_OK;
 }
 
-extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, void* stream) {
-    if (!out || blocks < 1 || iters < 0) return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe", cudaSuccess);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (kind) {
-        case 0: peak_probe_kernel<0><<<blocks, 256, 0, st>>>((long)iters, out); break;
-        case 1: peak_probe_kernel<1><<<blocks, 256, 0, st>>>((long)iters, out); break;
-        case 2: peak_probe_kernel<2><<<blocks, 256, 0, st>>>((long)iters, out); break;
-        case 3: peak_probe_kernel<3><<<blocks, 256, 0, st>>>((long)iters, out); break;
-        case 4: dmma_probe_kernel<<<blocks, 256, 0, st>>>((long)iters, out); break;
-        case 5: mix_probe_kernel<8, 1><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 1 DMMA
-        case 6: mix_probe_kernel<8, 2><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 2 DMMA
-        case 7: mix_probe_kernel<8, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA
-        case 8: mix_probe_kernel<0, 2><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 2 DMMA
-        case 9: mix_probe_kernel<8, 4><<<blocks, 256, 0, st>>>((long)iters, out); break;   // 8 DFMA + 4 DMMA
-        case 10: issue_probe_kernel<0, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA, 3 registers
-        case 11: issue_probe_kernel<1, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DADD
-        case 12: issue_probe_kernel<2, 0, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DMUL
-        case 13: issue_probe_kernel<0, 1, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 1 int
-        case 14: issue_probe_kernel<0, 2, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 2 int
-        case 15: issue_probe_kernel<0, 3, 0><<<blocks, 256, 0, st>>>((long)iters, out); break;  // DFMA + 3 int
-        case 16: issue_probe_kernel<0, 1, 1><<<blocks, 256, 0, st>>>((long)iters, out); break;  // 2 DFMA + 1 int + 1 LDS (+addr)
-        case 20: eval_probe_kernel<0><<<blocks, 128, 0, st>>>((long)iters, out); break;
-        case 21: eval_probe_kernel<1><<<blocks, 128, 0, st>>>((long)iters, out); break;
-        case 22: eval_probe_kernel<2><<<blocks, 128, 0, st>>>((long)iters, out); break;
-        case 23: eval_probe_kernel<3><<<blocks, 128, 0, st>>>((long)iters, out); break;
-        default: return svgpfa_set_error(SVGPFA_E_ARG, "peak_probe kind", cudaSuccess);
-    }
-    SVGPFA_CHECK_LAUNCH("peak_probe");
-    return SVGPFA_OK;
-}
 extern "C" const char* svgpfa_last_error(void) { return g_err; }
 
-extern "C" int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream) {
-    if (!x || !y_fast || !y_ref || n < 0) return svgpfa_set_error(SVGPFA_E_ARG, "exp_neg_eval", cudaSuccess);
-    if (n == 0) return SVGPFA_OK;
-    exp_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(x, y_fast, y_ref, (long)n);
-    SVGPFA_CHECK_LAUNCH("exp_neg_eval");
-    return SVGPFA_OK;
-}
-
-extern "C" int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream) {
-    if (!w2 || !y || n < 0) return svgpfa_set_error(SVGPFA_E_ARG, "exp2m_eval", cudaSuccess);
-    if (n == 0) return SVGPFA_OK;
-    exp2m_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(w2, y, (long)n);
-    SVGPFA_CHECK_LAUNCH("exp2m_eval");
-    return SVGPFA_OK;
+static int finalize_blocks(const svgpfa_dims* dims) {
+    size_t work = (size_t)dims->R * dims->KM;
+    int blocks = (int)((work + FIN_THREADS * 8 - 1) / (FIN_THREADS * 8));
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;
+    return blocks;
 }
 
 extern "C" int svgpfa_finalize(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     int rc = check_dims(dims, buf, "finalize");
     if (rc) return rc;
+    if (!buf->fin_part) return svgpfa_set_error(SVGPFA_E_ARG, "finalize: fin_part", cudaSuccess);
     cudaStream_t st = (cudaStream_t)stream;
-    size_t work = (size_t)dims->R * dims->KM;
-    int blocks = (int)((work + FIN_THREADS * 8 - 1) / (FIN_THREADS * 8));
-    if (blocks < 1) blocks = 1;
-    if (blocks > 592) blocks = 592;
+    const int blocks = finalize_blocks(dims);
     finalize_reduce_kernel<<<blocks, FIN_THREADS, 0, st>>>(*dims, *buf, flags, 1);
     SVGPFA_CHECK_LAUNCH("finalize_reduce");
-    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, 1);
+    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, blocks, 1);
     SVGPFA_CHECK_LAUNCH("finalize_combine");
     return SVGPFA_OK;
 }
@@ -328,14 +166,23 @@ namespace {
 // zero every accumulator of one evaluation (whole shard)
 void zero_accumulators(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool reuse_spike, cudaStream_t st) {
     const uint32_t kz = SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS;
-    cudaMemsetAsync(buf->shared, 0, sizeof(double) * shared_len(dims), st);
-    cudaMemsetAsync(buf->term1_part, 0, sizeof(double) * SVGPFA_TERM1_SLOTS, st);
-    cudaMemsetAsync(buf->info, 0, sizeof(int32_t) * 4, st);
-    if (!reuse_spike) cudaMemsetAsync(buf->abar_spk, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
+    ZeroList zl;
+    zl.cnt = 0;
+    auto add = [&](void* p, size_t n) { if (p && n) { zl.p[zl.cnt] = (double*)p; zl.n[zl.cnt] = n; ++zl.cnt; } };
+    add(buf->shared, shared_len(dims));
+    add(buf->term1_part, SVGPFA_TERM1_SLOTS);
+    add(buf->info, 2);                                  // 4 x int32
+    size_t big = 0;
+    if (!reuse_spike) { add(buf->abar_spk, (size_t)dims->R * dims->KM); big += (size_t)dims->R * dims->KM; }
     if (flags & kz) {
-        cudaMemsetAsync(buf->dz_acc, 0, sizeof(double) * (size_t)dims->R * dims->KM, st);
-        cudaMemsetAsync(buf->dth_part, 0, sizeof(double) * (size_t)dims->R * dims->TH, st);
+        add(buf->dz_acc, (size_t)dims->R * dims->KM);
+        add(buf->dth_part, (size_t)dims->R * dims->TH);
+        big += (size_t)dims->R * (dims->KM + dims->TH);
     }
+    size_t blocks = (big + shared_len(dims) + 256 * 8 - 1) / (256 * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1184) blocks = 1184;
+    zero_kernel<<<(unsigned)blocks, 256, 0, st>>>(zl);
 }
 
 // the seven per-trial stages on the trial range of `dims` (r0, rn); stage events only when `mark`
@@ -388,17 +235,21 @@ extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* b
 extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     int rc = check_dims(dims, buf, "cached_ell_fwd_bwd");
     if (rc) return rc;
+    if (!buf->fin_part) return svgpfa_set_error(SVGPFA_E_ARG, "cached_ell_fwd_bwd: fin_part", cudaSuccess);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(buf->shared, 0, sizeof(double) * shared_len(dims), st);
-    cudaMemsetAsync(buf->term1_part, 0, sizeof(double) * SVGPFA_TERM1_SLOTS, st);
+    ZeroList zl;
+    zl.cnt = 2;
+    zl.p[0] = buf->shared; zl.n[0] = shared_len(dims);
+    zl.p[1] = buf->term1_part; zl.n[1] = SVGPFA_TERM1_SLOTS;
+    zero_kernel<<<8, 256, 0, st>>>(zl);
     rc = svgpfa_quad_embed_fwd_bwd(dims, buf, SVGPFA_GRAD_EMBEDDING, stream); if (rc) return rc;
     rc = svgpfa_launch_spike_gather(dims, buf, st); if (rc) return rc;
-    // term1 and the d part of term2; no KL, no alpha.abar (the gather produced the C part)
+    // term1 and the d part of term2; no KL, no alpha.abar (the gather produced the C part in shared[4])
     svgpfa_dims d0 = *dims;
     d0.R = 0;                                   // empties the kl_rk loop; the alpha.abar loop is off (use_abar = 0)
     finalize_reduce_kernel<<<8, FIN_THREADS, 0, st>>>(d0, *buf, SVGPFA_GRAD_EMBEDDING, 0);
     SVGPFA_CHECK_LAUNCH("cached finalize_reduce");
-    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, 0);
+    finalize_combine_kernel<<<1, 32, 0, st>>>(*buf, 8, 0);
     SVGPFA_CHECK_LAUNCH("cached finalize_combine");
     return SVGPFA_OK;
 }
@@ -455,6 +306,30 @@ HostPipe* host_pipe() {
 
 }  // namespace
 
+extern "C" int svgpfa_release_thread_resources(void) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int dev = 0; dev < 16; ++dev) {
+        HostPipe& p = g_pipes[dev];
+        if (!p.init) continue;
+        cudaSetDevice(dev);
+        cudaStreamDestroy(p.in);
+        cudaStreamDestroy(p.out);
+        cudaStreamDestroy(p.comp2);
+        cudaEventDestroy(p.comp2_done);
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.drained);
+        for (int i = 0; i < HP_MAX_BLOCKS; ++i) {
+            cudaEventDestroy(p.copied[i]);
+            cudaEventDestroy(p.done[i]);
+        }
+        p = HostPipe();
+    }
+    cudaSetDevice(cur);
+    g_stage_events = nullptr;
+    return SVGPFA_OK;
+}
+
 extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffers* dev, const svgpfa_host_io* io,
                                      uint32_t flags, void* stream) {
     int rc = check_dims(dims, dev, "elbo_grad_host");
@@ -497,11 +372,8 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
         cudaStreamWaitEvent(s_in, hp->start, 0);
     }
     // Odd blocks run their kernels on a second compute stream, so that the tail wave of one block's kernels overlaps
-    // the next block's (20000 trials: 274.0 -> 269.6 ms, 2500 trials: 36.3 -> 35.4 ms; SVGPFA_HOST_STREAMS=1 switches
-    // it off).  Both streams accumulate into `shared` with atomics; per-trial outputs never overlap.
-    static int two_streams = -1;
-    if (two_streams < 0) { const char* e = getenv("SVGPFA_HOST_STREAMS"); two_streams = (e && atoi(e) == 1) ? 0 : 1; }
-    const bool two = hp && two_streams;
+    // the next block's (20000 trials: 274.0 -> 269.6 ms, 2500 trials: 36.3 -> 35.4 ms).  Both streams accumulate into `shared` with atomics; per-trial outputs never overlap.
+    const bool two = hp != nullptr;
     if (two) cudaStreamWaitEvent(hp->comp2, hp->start, 0);
     auto r_of = [&](int b) { return (size_t)(R * (size_t)b / (size_t)nb); };
     // K-major arrays: the block's trials are K separate runs, one per latent; with a uniform M they form a 2-D copy

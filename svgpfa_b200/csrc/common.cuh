@@ -4,6 +4,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "svgpfa_b200.h"
 
 #include "exp_table.cuh"
@@ -311,6 +313,40 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 inline int svgpfa_ntrials(const svgpfa_dims* d) { return SVGPFA_NTRIALS(d); }
+
+// Launch-path housekeeping done ONCE per (call site / template instantiation, device) instead of on every launch
+// (function attributes are per device and context; cudaFuncSetAttribute and the occupancy query cost several
+// microseconds each and used to sit in front of every kernel of every evaluation).  Idempotent bodies only: two host
+// threads racing on the first launch both run the body.
+#define SVGPFA_ONCE_PER_DEVICE(...)                                                     \
+    do {                                                                                \
+        static std::atomic<uint64_t> done_{0};                                          \
+        int dev_ = 0;                                                                   \
+        cudaGetDevice(&dev_);                                                           \
+        const uint64_t bit_ = 1ull << (dev_ & 63);                                      \
+        if (!(done_.load(std::memory_order_acquire) & bit_)) {                          \
+            __VA_ARGS__;                                                                \
+            done_.fetch_or(bit_, std::memory_order_release);                            \
+        }                                                                               \
+    } while (0)
+
+// Dynamic shared-memory opt-in of a kernel, raised only when a launch needs more than any earlier one on this device.
+// Usage: SVGPFA_ENSURE_SMEM(bytes, kernel<template, args>);
+#define SVGPFA_ENSURE_SMEM(bytes, ...)                                                                          \
+    do {                                                                                                        \
+        static std::atomic<size_t> cur_[64];                                                                    \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        if (cur_[dev_ & 63].load(std::memory_order_acquire) < (size_t)(bytes)) {                                \
+            cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
+            cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout,                   \
+                                 cudaSharedmemCarveoutMaxShared);                                               \
+            cur_[dev_ & 63].store((size_t)(bytes), std::memory_order_release);                                  \
+        }                                                                                                       \
+    } while (0)
+
+// multiprocessor count of the current device, cached per device (api.cu)
+int svgpfa_sm_count();
 
 // host-side error plumbing (api.cu)
 int svgpfa_set_error(int code, const char* where, cudaError_t ce);

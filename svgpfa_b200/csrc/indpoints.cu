@@ -5,8 +5,6 @@
 //   indpoints_bwd_kernel  adjoints through alpha, c, X, KL and the Cholesky factorisation
 // Reference arithmetic: stats/kernelsMatricesStore.py:107-138, utils/miscUtils.py:135-155,209-216,
 // stats/klDivergence.py:31-44; adjoints per SURVEY.md Appendix A (the reference uses autograd).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace {
@@ -492,12 +490,6 @@ __global__ void __launch_bounds__(IP_BWD_THREADS) indpoints_bwd_kernel(svgpfa_di
     }
 }
 
-int ip_bwd_threads() {          // SVGPFA_IPBWD_THREADS (experiments): 128 or 256
-    static int t = 0;
-    if (!t) { const char* e = getenv("SVGPFA_IPBWD_THREADS"); t = e ? atoi(e) : IP_BWD_THREADS; if (t != 32 && t != 64 && t != 128 && t != 256) t = IP_BWD_THREADS; }
-    return t;
-}
-
 size_t ip_smem(int Mmax, int nmat, int nvec) {
     const int MP = (Mmax + 7) / 8 * 8, ld = MP + 4;      // covers both the odd-ld (M|1) and the padded (MP+4) layouts
     return sizeof(double) * ((size_t)nmat * MP * ld + (size_t)nvec * MP);
@@ -509,17 +501,12 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M || dims->Mmax < 1) return svgpfa_set_error(SVGPFA_E_ARG, "kzz_chol_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 2, 2);
-    static int variant = -1;                        // SVGPFA_CHOL_VARIANT=1: the shared-memory kernel also for M <= 32
-    if (variant < 0) { const char* e = getenv("SVGPFA_CHOL_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (dims->Mmax <= 32 && variant != 1) {
+    if (dims->Mmax <= 32) {
         const int nprob = svgpfa_ntrials(dims) * dims->K;
         const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
         kzz_chol_warp_kernel<<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
-    } else if (dims->Mmax <= 32) {
-        cudaFuncSetAttribute(kzz_chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kzz_chol_kernel<true><<<dim3(svgpfa_ntrials(dims), dims->K), 32, smem, (cudaStream_t)stream>>>(*dims, *buf);
     } else {
-        cudaFuncSetAttribute(kzz_chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SVGPFA_ENSURE_SMEM(smem, kzz_chol_kernel<false>);
         kzz_chol_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
     }
     SVGPFA_CHECK_LAUNCH("kzz_chol_fwd");
@@ -529,15 +516,13 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
 extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "indpoints_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    static int variant = -1;                        // SVGPFA_IPFWD_VARIANT=1: the CTA-per-matrix kernel also for M <= 32
-    if (variant < 0) { const char* e = getenv("SVGPFA_IPFWD_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (dims->Mmax <= 32 && variant != 1) {
+    if (dims->Mmax <= 32) {
         const int nprob = svgpfa_ntrials(dims) * dims->K;
         const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
         indpoints_fwd_warp_kernel<<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
     } else {
         const size_t smem = ip_smem(dims->Mmax, 2, 2);
-        cudaFuncSetAttribute(indpoints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SVGPFA_ENSURE_SMEM(smem, indpoints_fwd_kernel);
         indpoints_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     }
     SVGPFA_CHECK_LAUNCH("indpoints_fwd");
@@ -548,9 +533,8 @@ extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "indpoints_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
     const size_t smem = ip_smem(dims->Mmax, 6, 6);
-    cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(indpoints_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), ip_bwd_threads(), smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    SVGPFA_ENSURE_SMEM(smem, indpoints_bwd_kernel);
+    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_BWD_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;
 }

@@ -5,8 +5,6 @@
 // Ktz (R,Q,M), Kzz^-1 Kzt (R,M,Q) and eLinkValues (R,Q,N) of the reference are never materialised
 // (stats/kernelsMatricesStore.py:186-195, stats/svPosteriorOnLatents.py:185-216,
 //  stats/svEmbedding.py:80-84, stats/expectedLogLikelihood.py:107-135,205-208).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
@@ -14,11 +12,8 @@ bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* b
 
 bool svgpfa_try_quad_embed_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st);
 
-static bool use_mma_path() {
-    static int v = -1;
-    if (v < 0) v = getenv("SVGPFA_NO_MMA") ? 0 : 1;       // experiments only: force the CUDA-core kernels
-    return v == 1;
-}
+// The tensor-path kernels (quad_mma.cu) cover M <= 32 and K <= 39; the kernels in this file are the general path.
+static bool use_mma_path() { return true; }
 
 namespace {
 
@@ -586,8 +581,7 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
         return SVGPFA_OK;
     }
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, false);
-    cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(quad_latent_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    SVGPFA_ENSURE_SMEM(smem, quad_latent_fwd_kernel);
     quad_latent_fwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf);
     SVGPFA_CHECK_LAUNCH("quad_latent_fwd");
     return SVGPFA_OK;
@@ -603,11 +597,10 @@ extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buff
     const size_t smem = sizeof(double) * ql_smem_doubles(dims->Mmax, true);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_latent_bwd: shared memory", cudaSuccess);
     if (dims->Mmax > 44) {
-        cudaFuncSetAttribute(quad_latent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SVGPFA_ENSURE_SMEM(smem, quad_latent_bwd_kernel<true>);
         quad_latent_bwd_kernel<true><<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     } else {
-        cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(quad_latent_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        SVGPFA_ENSURE_SMEM(smem, quad_latent_bwd_kernel<false>);
         quad_latent_bwd_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), QL_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
     }
     SVGPFA_CHECK_LAUNCH("quad_latent_bwd");
@@ -623,15 +616,12 @@ extern "C" int svgpfa_quad_embed_fwd_bwd(const svgpfa_dims* dims, const svgpfa_b
     }
     const size_t smem = em_smem_bytes(dims->K);
     if (smem > 227 * 1024) return svgpfa_set_error(SVGPFA_E_UNSUPPORTED, "quad_embed: K too large for shared memory", cudaSuccess);
-    cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(quad_embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    SVGPFA_ENSURE_SMEM(smem, quad_embed_kernel);
     const int ntiles = (dims->N + EM_TN - 1) / EM_TN;
     const int qtiles = (dims->Q + EM_TQ - 1) / EM_TQ;
     const long nitems = (long)svgpfa_ntrials(dims) * qtiles;
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    int occ = 2;
+    const int nsm = svgpfa_sm_count();
+    int occ = 2;              // general path only (K > 39): the query runs per launch
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_kernel, EM_THREADS, smem);
     if (occ < 1) occ = 1;
     long workers = (long)nsm * occ / ntiles;           // one resident wave of persistent CTAs

@@ -396,9 +396,7 @@ void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flag
     if (nw > QM_WARPS) nw = QM_WARPS;
     if (nw < 1) nw = 1;
     const size_t smem = sizeof(double) * qm_smem_doubles(8 * MT, nw, BWD);
-    cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(quad_latent_mma_kernel<MT, BWD>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
+    SVGPFA_ENSURE_SMEM(smem, quad_latent_mma_kernel<MT, BWD>);
     quad_latent_mma_kernel<MT, BWD><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
 }
 
@@ -610,17 +608,23 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
 
 template <int KT>
 void launch_emm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
-    const size_t smem = sizeof(double) * emm_smem_doubles(dims->K);
-    cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // shared memory depends on KP = 8 KT only, so the attribute and the occupancy are fixed per instantiation
+    const size_t smem = sizeof(double) * emm_smem_doubles(8 * KT - 1);
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = occ_cache[dev & 63].load(std::memory_order_relaxed);
+    if (occ <= 0) {
+        cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(quad_embed_mma_kernel<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_mma_kernel<KT>, EMM_THREADS, smem);
+        if (occ < 1) occ = 1;
+        occ_cache[dev & 63].store(occ, std::memory_order_relaxed);
+    }
     const int ntiles = (dims->N + EMM_TN - 1) / EMM_TN;
     const int qtiles = (dims->Q + EMM_TQ - 1) / EMM_TQ;
     const long nitems = (long)svgpfa_ntrials(dims) * qtiles;
-    int dev = 0, nsm = 148, occ = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_mma_kernel<KT>, EMM_THREADS, smem);
-    if (occ < 1) occ = 1;
+    const int nsm = svgpfa_sm_count();
     long workers = (long)nsm * occ / ntiles;
     if (workers < 1) workers = 1;
     if (workers > nitems) workers = nitems;

@@ -6,20 +6,17 @@
 // exponential link never uses the spike-time variance, expectedLogLikelihood.py:210-213),
 // stats/svEmbedding.py:137-144.  Ktz[k][r] (S_r x M) is never materialised.
 //
-// Mapping of spike_fwd_bwd_kernel: a warp owns 32 consecutive (latent, inducing point) pairs of one trial
+// Mapping of spike_tile_kernel: a warp owns 32 consecutive (latent, inducing point) pairs of one trial
 // -- z_j, alpha_j and the kernel constants live in registers -- and walks the spikes of a range of neurons.
 // Spikes are stored neuron-major inside a trial, so the embedding weight C[n,k] is constant over a segment:
 //   pn_j(n)   = sum_{s in (r,n)} kappa(t_s - z_j)
 //   abar_j    = sum_n C[n,k] pn_j(n)          (no cross-lane traffic)
 //   dC[n,k]  += sum_j alpha_j pn_j(n)         (one segmented warp reduction per NON-EMPTY segment)
 // and the value of the term is alpha . abar (taken in svgpfa_finalize).
-#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
-
-constexpr int SP_WPB = 4;     // warps per CTA
 
 // segmented (by latent) sum over the lanes of a warp; valid in the first lane of every segment
 __device__ __forceinline__ double seg_sum(double v, unsigned same_mask) {
@@ -29,76 +26,6 @@ __device__ __forceinline__ double seg_sum(double v, unsigned same_mask) {
         if (same_mask & (1u << b)) v += o;
     }
     return v;
-}
-
-// One kernel evaluation and its accumulations for one (spike, inducing point).
-//   pn += kappa;  expquad : p1 += kappa d,              p2 += kappa d^2
-//                 periodic: p1 += kappa sin(2 pi d/p),  p2 += kappa sin^2(pi d/p),  p3 += kappa sin(2 pi d/p) d
-template <bool KGRAD, bool PERIODIC>
-__device__ __forceinline__ void spike_eval(double t, double z, double nh, double invp,
-                                           const double* __restrict__ etab, double& pn, double& p1, double& p2,
-                                           double& p3) {
-    const double dl = t - z;
-    if (!PERIODIC) {
-        const double q = dl * dl;
-        const double kv = svgpfa_exp_neg(nh * q, etab);
-        pn += kv;
-        if (KGRAD) {
-            p1 = fma(kv, dl, p1);
-            p2 = fma(kv, q, p2);
-        }
-    } else {
-        double sn, cs;
-        sincospi(dl * invp, &sn, &cs);
-        const double q = sn * sn;
-        const double kv = svgpfa_exp_neg(nh * q, etab);
-        pn += kv;
-        if (KGRAD) {
-            const double w = kv * (2.0 * sn * cs);
-            p1 += w;
-            p2 = fma(kv, q, p2);
-            p3 = fma(w, dl, p3);
-        }
-    }
-}
-
-// All spikes of one (trial, neuron) segment for the NP (latent, inducing point) pairs of one lane.  UNROLL spike
-// times are loaded one iteration ahead of their use (software pipelining: the loads are warp-uniform L1 hits, but
-// their latency would otherwise sit in front of every dependent FP64 chain).
-template <bool KGRAD, bool PERIODIC, int UNROLL, int NP>
-__device__ __forceinline__ void spike_segment(const double* __restrict__ sp, int cnt, const double (&z)[NP],
-                                              const double (&nh)[NP], const double (&invp)[NP],
-                                              const double* __restrict__ etab, double (&pn)[NP], double (&p1)[NP],
-                                              double (&p2)[NP], double (&p3)[NP]) {
-    int i = 0;
-    if (cnt >= UNROLL) {
-        double tn[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) tn[u] = sp[u];
-        for (; i + UNROLL <= cnt; i += UNROLL) {
-            double tc[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) tc[u] = tn[u];
-            if (i + 2 * UNROLL <= cnt) {
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) tn[u] = sp[i + UNROLL + u];
-            }
-            // pull the line 32 spikes ahead into L1 (segments of a trial are contiguous, so this also warms the
-            // next segments); without it every fourth iteration waits on an L2 round trip
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + i + 32));
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                for (int p = 0; p < NP; ++p)
-                    spike_eval<KGRAD, PERIODIC>(tc[u], z[p], nh[p], invp[p], etab, pn[p], p1[p], p2[p], p3[p]);
-        }
-    }
-    for (; i < cnt; ++i) {
-        const double t = sp[i];
-#pragma unroll
-        for (int p = 0; p < NP; ++p)
-            spike_eval<KGRAD, PERIODIC>(t, z[p], nh[p], invp[p], etab, pn[p], p1[p], p2[p], p3[p]);
-    }
 }
 
 // Lane-local description of one (latent, inducing point) pair.
@@ -152,114 +79,10 @@ __device__ __forceinline__ int slot_to_pair(const svgpfa_dims& dm, const svgpfa_
     return dm.KM;
 }
 
-// NP = (latent, inducing point) pairs per lane: slot p of a warp covers pairs grp*32*NP + p*32 + lane, so the
-// spike load, the loop and the segment bookkeeping are shared by NP kernel evaluations.
-// UNROLL = spikes per software-pipelined iteration, MINB = resident CTAs per SM asked of ptxas.
-template <bool KGRAD, int UNROLL, int MINB, int NP>
-__global__ void __launch_bounds__(32 * SP_WPB, MINB) spike_fwd_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf,
-                                                                          uint32_t flags, int n_chunks, int chunk) {
-    __shared__ double etab[SVGPFA_EXP_TAB_SIZE];
-    svgpfa_load_exp_tab(etab);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
-    const int grp = blockIdx.y * SP_WPB + warp;
-    if (grp * 32 * NP >= dm.KM) return;                  // whole warp out of range
-    PairInfo pi[NP];
-    double z[NP], nh[NP], invp[NP], a[NP];
-    bool any_periodic = false, all_periodic = true;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        pi[p] = pair_info(dm, bf, grp * 32 * NP + p * 32 + lane, lane);
-        const svgpfa_latent_desc ds = bf.desc[pi[p].k];
-        const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi[p].k);
-        const int l = pi[p].active ? pi[p].li : dm.KM - 1;
-        z[p] = bf.Z[(size_t)dm.R * ds.moff + (size_t)r * ds.M + (l - ds.moff)];
-        nh[p] = kc.nh;
-        invp[p] = kc.invp;
-        a[p] = pi[p].active ? kc.s2 * bf.alpha[(size_t)r * dm.KM + pi[p].li] : 0.0;     // scale^2 alpha_j
-        const bool per = kc.type == SVGPFA_KERNEL_PERIODIC;
-        any_periodic |= per;
-        all_periodic &= per;
-    }
-    // a lane whose NP pairs mix kernel types takes the general (periodic-capable) path for all of them: the
-    // periodic formula with invp = 0 is NOT the exponential-quadratic one, so mixed lanes evaluate pair by pair
-    const bool mixed = any_periodic && !all_periodic;
-    const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
-    const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
-    const int64_t* __restrict__ seg = bf.seg_off + (size_t)r * dm.N;
-    const double* __restrict__ st = bf.spike_t;
-    double* gC = bf.shared + SVGPFA_SHARED_HDR;
-    double abar[NP], dz[NP], d0[NP], d1[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) abar[p] = dz[p] = d0[p] = d1[p] = 0.0;
-    int64_t s1 = seg[nb];
-    for (int n = nb; n < ne; ++n) {
-        const int64_t s0 = s1;
-        s1 = seg[n + 1];
-        const int cnt = (int)(s1 - s0);
-        if (cnt == 0) continue;
-        double c[NP], pn[NP], p1[NP], p2[NP], p3[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            c[p] = bf.C[(size_t)n * dm.K + pi[p].k];
-            pn[p] = p1[p] = p2[p] = p3[p] = 0.0;
-        }
-        if (!any_periodic) {
-            spike_segment<KGRAD, false, UNROLL, NP>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
-        } else if (!mixed) {
-            spike_segment<KGRAD, true, UNROLL, NP>(st + s0, cnt, z, nh, invp, etab, pn, p1, p2, p3);
-        } else {
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const double z1[1] = {z[p]}, nh1[1] = {nh[p]}, ip1[1] = {invp[p]};
-                double q0[1] = {0.0}, q1[1] = {0.0}, q2[1] = {0.0}, q3[1] = {0.0};
-                if (invp[p] == 0.0) spike_segment<KGRAD, false, UNROLL, 1>(st + s0, cnt, z1, nh1, ip1, etab, q0, q1, q2, q3);
-                else spike_segment<KGRAD, true, UNROLL, 1>(st + s0, cnt, z1, nh1, ip1, etab, q0, q1, q2, q3);
-                pn[p] = q0[0]; p1[p] = q1[0]; p2[p] = q2[0]; p3[p] = q3[0];
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            abar[p] = fma(c[p], pn[p], abar[p]);
-            if (KGRAD) {
-                dz[p] = fma(c[p], p1[p], dz[p]);
-                d0[p] = fma(c[p], p2[p], d0[p]);
-                d1[p] = fma(c[p], p3[p], d1[p]);
-            }
-            if (need_emb) {
-                const double v = seg_sum(pn[p] * a[p], pi[p].same);
-                if (pi[p].head) atomicAdd(gC + (size_t)n * dm.K + pi[p].k, v);
-            }
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        const svgpfa_latent_desc ds = bf.desc[pi[p].k];
-        const KConst kc = make_kconst(ds, bf.theta, bf.kscale, pi[p].k);
-        if (pi[p].active) {
-            atomicAdd(bf.abar_spk + (size_t)r * dm.KM + pi[p].li, kc.s2 * abar[p]);
-            // kbar_sj = C alpha_j ; d delta/dz = -1 ; dkappa/ddelta = kappa * (delta | sin 2 pi d/p) * dd
-            if (KGRAD && (flags & SVGPFA_GRAD_INDLOCS))
-                atomicAdd(bf.dz_acc + (size_t)r * dm.KM + pi[p].li, -a[p] * kc.dd * dz[p]);
-        }
-        if (KGRAD && (flags & SVGPFA_GRAD_KERNEL)) {
-            // dkappa/dtheta0 = kappa (d^2 | sin^2) dl (p2);  periodic: dkappa/dtheta1 = kappa sin(2 pi d/p) d dp (p3)
-            const double t0 = seg_sum(pi[p].active ? a[p] * kc.dl * d0[p] : 0.0, pi[p].same);
-            const double t1 = seg_sum(pi[p].active ? a[p] * kc.dp * d1[p] : 0.0, pi[p].same);
-            if (pi[p].head) {
-                double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-                atomicAdd(dth, t0);
-                if (ds.nth > 1) atomicAdd(dth + 1, t1);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// spike_tile_kernel: the same term with the spikes of the CTA's neuron range staged through SHARED memory and a
-// leaner inner loop (13 FP64 + ~5 other instructions per (spike, inducing point)).  What the ncu captures of the
-// kernel above showed, and what this one does about it:
+// spike_tile_kernel: the spikes of the CTA's neuron range are staged through SHARED memory; the inner loop is
+// 13 FP64 + ~5 other instructions per (spike, inducing point).  What the ncu captures of the first version (spike
+// times and a 2048-entry exp table read with plain loads; removed) showed, and what this kernel does about it:
 //   * its 2048-entry exp table cost ~6 shared-memory wavefronts per warp lookup (random 8-byte gathers; LSU data
 //     pipe 80 % busy)  ->  svgpfa_exp2m: 256 entries x 16 replicas, conflict-free by construction (common.cuh);
 //   * the warps of a CTA own 128 consecutive pairs of ONE trial and walk the same spikes, so a tile of ST_TILE spike
@@ -719,7 +542,7 @@ static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, in
     const long target_warps = (long)nsm * 64 * 4 / np;
     const long Rn = svgpfa_ntrials(dims);
     long n_chunks = (target_warps + Rn * LG - 1) / (Rn * LG);
-    if (const char* e = getenv("SVGPFA_SPIKE_CHUNKS")) n_chunks = atol(e);     // tests: force long neuron ranges
+    if (dims->spike_chunks > 0) n_chunks = dims->spike_chunks;                 // tests: force long neuron ranges
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > dims->N) n_chunks = dims->N;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
@@ -730,28 +553,14 @@ static void spike_grid(const svgpfa_dims* dims, int nsm, int np, int min_wpb, in
     *chunk_out = chunk;
 }
 
-// SVGPFA_SPIKE_VARIANT (environment, experiments only): 1 = the register/global-load kernel (spike_fwd_bwd_kernel);
-// 12 = spike_tile_kernel with 2 pairs per lane, 96 = 1 pair per lane with a 96-register budget; default = 1 pair
-// per lane, 128 registers (4 CTAs per SM).  Measured on B200, config #5 shard of 2000 trials (ms): 1 -> 17.16,
-// 96 -> 15.92, default -> 15.22, 12 -> 16.43, 4 pairs per lane -> 18.4 (dropped).
-static int spike_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SVGPFA_SPIKE_VARIANT");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
-
+// One pair per lane, 128 threads, 128 registers (4 CTAs per SM).  Measured on B200, config #5 shard of 2000 trials
+// (ms): the first register/global-load kernel 17.16, 96-register build 15.92, this one 15.22 -> 14.05, 2 pairs per
+// lane 16.43, 4 pairs per lane 18.4 (profiles/README.md; the slower variants are no longer built).
 template <int NP, int MAXT, int MAXR>
 static void launch_tile(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st, int nsm,
                         bool kgrad) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(spike_tile_kernel<true, NP, MAXT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
-        cudaFuncSetAttribute(spike_tile_kernel<false, NP, MAXT, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
-        attr_set = true;
-    }
+    SVGPFA_ENSURE_SMEM(ST_SMEM, spike_tile_kernel<true, NP, MAXT, MAXR>);
+    SVGPFA_ENSURE_SMEM(ST_SMEM, spike_tile_kernel<false, NP, MAXT, MAXR>);
     dim3 grid;
     int wpb, n_chunks, chunk;
     spike_grid(dims, nsm, NP, MAXT >= 256 ? 4 : (MAXT / 32 < 4 ? MAXT / 32 : 4), MAXT / 32, true, &grid, &wpb, &n_chunks, &chunk);
@@ -767,27 +576,8 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
     if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd", cudaSuccess);
     if (dims->R == 0 || dims->S == 0 || dims->N == 0) return SVGPFA_OK;
     if (!dims->desc_host) return svgpfa_set_error(SVGPFA_E_ARG, "spike_fwd_bwd: dims.desc_host", cudaSuccess);
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaStream_t st = (cudaStream_t)stream;
     const bool kgrad = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
-    int var = spike_variant();
-    if (var == 1) {     // measured on B200, config #5 shard of 2000 trials: 17.1 ms (profiles/README.md)
-        dim3 grid;
-        int wpb, n_chunks, chunk;
-        spike_grid(dims, nsm, 1, SP_WPB, SP_WPB, false, &grid, &wpb, &n_chunks, &chunk);
-        grid.y = ((dims->KM + 31) / 32 + SP_WPB - 1) / SP_WPB;
-        if (kgrad) spike_fwd_bwd_kernel<true, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
-        else spike_fwd_bwd_kernel<false, 4, 6, 1><<<grid, 32 * SP_WPB, 0, st>>>(*dims, *buf, flags, n_chunks, chunk);
-    } else {
-        // NP = 2 needs every M_k even (the pairs of a lane share the latent)
-        bool even = true;
-        for (int k = 0; k < dims->K; ++k) even = even && (dims->desc_host[k].M % 2 == 0);
-        if (var == 12 && even) launch_tile<2, 160, 96>(dims, buf, flags, st, nsm, kgrad);
-        else if (var == 96) launch_tile<1, 128, 96>(dims, buf, flags, st, nsm, kgrad);
-        else launch_tile<1, 128, 128>(dims, buf, flags, st, nsm, kgrad);
-    }
+    launch_tile<1, 128, 128>(dims, buf, flags, (cudaStream_t)stream, svgpfa_sm_count(), kgrad);
     SVGPFA_CHECK_LAUNCH("spike_fwd_bwd");
     return SVGPFA_OK;
 }
@@ -795,14 +585,12 @@ extern "C" int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffer
 extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf) return svgpfa_set_error(SVGPFA_E_ARG, "spike_latent_means", cudaSuccess);
     if (dims->R == 0 || dims->S == 0) return SVGPFA_OK;
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int nsm = svgpfa_sm_count();
     const int Rn = svgpfa_ntrials(dims);
     int n_split = (nsm * 8 + Rn - 1) / Rn;
     if (n_split < 1) n_split = 1;
     const size_t smem = SVGPFA_EXP2M_TAB_BYTES + sizeof(double) * (2 * (size_t)dims->KM + 2 * (size_t)dims->K);
-    cudaFuncSetAttribute(spike_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SVGPFA_ENSURE_SMEM(smem, spike_means_kernel);
     spike_means_kernel<<<Rn * n_split, SM_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, n_split);
     SVGPFA_CHECK_LAUNCH("spike_latent_means");
     return SVGPFA_OK;
@@ -810,9 +598,7 @@ extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_b
 
 int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t stream) {
     if (dims->R == 0 || dims->S == 0) return SVGPFA_OK;
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int nsm = svgpfa_sm_count();
     const long nseg = (long)svgpfa_ntrials(dims) * dims->N;
     long blocks = (nseg + SG_THREADS / 32 - 1) / (SG_THREADS / 32);
     if (blocks > (long)nsm * 16) blocks = (long)nsm * 16;

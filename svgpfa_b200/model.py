@@ -11,7 +11,16 @@ Differences a user can observe, all deliberate:
   * value and gradients are produced by ONE fused forward+backward pass (the bound is a sum,
     its upstream gradient is a scalar applied in ``backward``);
   * a non-positive-definite Kzz raises ``torch.linalg.LinAlgError`` from ``eval()``
-    (the reference raises it from ``buildKernelsMatrices``, utils/miscUtils.py:215).
+    (the reference raises it from ``buildKernelsMatrices``, utils/miscUtils.py:215).  The error state
+    travels with the bound in the 8-double header of the result buffer, which is copied to pinned host
+    memory asynchronously: a forward-only ``eval()`` checks it before returning; an evaluation that will
+    be differentiated (an optimiser closure) is checked when its copy has landed -- at the latest on the
+    next call into the model -- so the host never stalls between ``eval()`` and ``backward()``.
+    ``checkErrors()`` forces the check;
+  * with a ``process_group`` (one rank per GPU, trials sharded) an evaluation all-reduces the packed
+    ``[elbo.. | dC | dd | dtheta]`` buffer, except while ONLY per-trial leaves (m, cholVecs, Z) require
+    gradients: the bound is separable over trials given (C, d, theta), so each rank then optimises its own
+    block with no collective inside the closure (``shard_mode``; SURVEY.md §8e option (i)).
 There is no CPU path: without a CUDA device or without the built library every entry raises.
 """
 from __future__ import annotations
@@ -58,12 +67,14 @@ class _LowerBoundFn(torch.autograd.Function):
         ctx.model = model
         ctx.flags = flags
         ctx.bufs = (shared, gZ, gm, gcv)
+        model._last_shared = shared
         ctx.d_shape = leaves[2 * K + 1].shape
         return shared[0].clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         model, flags = ctx.model, ctx.flags
+        model._poll_errors(block=False)
         shared, gZ, gm, gcv = ctx.bufs
         K, R, N = model._K, model._R, model._N
         need = ctx.needs_input_grad[2:]
@@ -98,10 +109,20 @@ class _LowerBoundFn(torch.autograd.Function):
 
 
 class B200SVLowerBound:
-    def __init__(self, kernels=None, device=None, process_group=None, check_errors=True):
+    _PENDING_SLOTS = 8
+
+    def __init__(self, kernels=None, device=None, process_group=None, check_errors=True, shard_mode="auto"):
         self._device = torch.device(device) if device is not None else None
         self._pg = process_group
+        if shard_mode not in ("auto", "reduce", "local"):
+            raise ValueError("shard_mode must be 'auto', 'reduce' or 'local'")
+        self.shard_mode = shard_mode
         self._check_errors = check_errors
+        self._pending = []                 # slots of the header copies in flight, oldest first
+        self._pinned = None
+        self._leaf_list = None
+        self._next_slot = 0
+        self._spike_chunks = 0             # tuning / tests: neuron ranges per trial in the spike kernel (0 = automatic)
         self._kernels = None
         self._reg = None
         self._params_set = False
@@ -133,6 +154,44 @@ class B200SVLowerBound:
     def setKernels(self, kernels):
         self._kernels = list(kernels)
         self._ready = False
+        self._kzz_key = self._spike_key = None
+        if self._params_set:               # kernels replaced after the parameters: re-derive what depends on them
+            if len(self._kernels) != self._K:
+                raise ValueError("inconsistent number of latents in kernels / initial_params")
+            self._bind_kernels()
+
+    def _bind_kernels(self):
+        """Kernel-dependent metadata (type, scale^2, parameter scalings) and the aliasing of every kernel object's
+        parameter tensor with its slice of the packed buffer."""
+        K, dev = self._K, self._dev()
+        specs = [kernel_spec(kern) for kern in self._kernels]
+        nth = [2 if s[0] == _cabi.KERNEL_PERIODIC else 1 for s in specs]
+        if getattr(self, "_nth", nth) != nth:
+            raise ValueError("kernel types do not match the packed kernel parameters; call setInitialParams again")
+        self._nth = nth
+        for k, kern in enumerate(self._kernels):
+            if hasattr(kern, "setParams"):
+                kern.setParams(self._theta[k])
+        desc = (_cabi.LatentDesc * K)()
+        for k in range(K):
+            desc[k] = _cabi.LatentDesc(specs[k][0], self._M[k], self._moff[k], self._mmoff[k], self._poff[k],
+                                       self._thoff[k], self._P[k], self._nth[k])
+        self._desc_host = desc
+        self._desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.int32).to(dev)
+        self._kscale = torch.tensor([[s[1], s[2], s[3], 0.0] for s in specs], dtype=_F64).to(dev).contiguous()
+
+    def _make_views(self):
+        """The leaf tensors the getters hand out: views of the packed K-major buffers (the optimiser's in-place
+        updates need no gather, and the kernels read the packed buffers directly)."""
+        R, K = self._R, self._K
+        self._Z = [self._Zbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
+        self._m = [self._mbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
+        self._cv = [self._cvbuf[R * self._poff[k]:R * self._poff[k + 1]].view(R, self._P[k], 1) for k in range(K)]
+        self._theta = [self._thbuf[self._thoff[k]:self._thoff[k + 1]] for k in range(K)]
+        self._leaf_list = None
+
+    def _refresh_leaf_list(self):
+        self._leaf_list = list(self._m) + list(self._cv) + [self._C, self._d] + list(self._theta) + list(self._Z)
 
     def setInitialParams(self, initial_params):
         """``initial_params`` as produced by ``svGPFA.utils.initUtils.getParamsAndKernelsTypes``
@@ -168,28 +227,16 @@ class B200SVLowerBound:
         self._moff, self._poff, self._thoff = cum(self._M), cum(self._P), cum(self._nth)
         self._mmoff = cum([M * M for M in self._M])
         self._KM, self._PP, self._TH, self._MM = self._moff[-1], self._poff[-1], self._thoff[-1], self._mmoff[-1]
-        dev = self._dev()
         pack = lambda xs: torch.cat([self._to_dev(x).reshape(-1) for x in xs]).contiguous()
         self._Zbuf, self._mbuf, self._cvbuf, self._thbuf = pack(Z0), pack(mean), pack(chol), pack(theta0)
-        self._Z = [self._Zbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
-        self._m = [self._mbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
-        self._cv = [self._cvbuf[R * self._poff[k]:R * self._poff[k + 1]].view(R, self._P[k], 1) for k in range(K)]
-        self._theta = [self._thbuf[self._thoff[k]:self._thoff[k + 1]] for k in range(K)]
-        for k, kern in enumerate(self._kernels):
-            if hasattr(kern, "setParams"):
-                kern.setParams(self._theta[k])
+        self._make_views()
         self._C = self._to_dev(C0).contiguous().clone()
         self._d = self._to_dev(d0).contiguous().clone()
         self._N = int(self._C.shape[0])
         if self._C.shape[1] != K or self._d.numel() != self._N:
             raise ValueError("C must be (N,K) and d must have N entries")
-        desc = (_cabi.LatentDesc * K)()
-        for k in range(K):
-            desc[k] = _cabi.LatentDesc(specs[k][0], self._M[k], self._moff[k], self._mmoff[k], self._poff[k],
-                                       self._thoff[k], self._P[k], self._nth[k])
-        self._desc_host = desc
-        self._desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.int32).to(dev)
-        self._kscale = torch.tensor([[s[1], s[2], s[3], 0.0] for s in specs], dtype=_F64).to(dev).contiguous()
+        self._bind_kernels()
+        self._refresh_leaf_list()
         self._params_set = True
         self._ready = False
         self._kzz_key = self._spike_key = None
@@ -240,7 +287,9 @@ class B200SVLowerBound:
 
     def setPriorCovRegParam(self, priorCovRegParam):
         self._reg = float(priorCovRegParam)
-        self._kzz_key = None
+        self._kzz_key = self._spike_key = None
+        if self._ready:
+            self._dims.reg = self._reg         # the value the kernels read
 
     def setParamsAndData(self, measurements, initial_params, eLLCalculationParams, priorCovRegParam):
         self.setMeasurements(measurements=measurements)
@@ -293,12 +342,14 @@ class B200SVLowerBound:
             mu_q=e(R * Q * K), var_q=e(R * Q * K), mubar_part=e(n_ntiles * R * Q * K),
             varbar_part=e(n_ntiles * R * Q * K),
             term1_part=torch.zeros(_cabi.TERM1_SLOTS, dtype=_F64, device=dev),
+            fin_part=torch.zeros(3 * _cabi.FIN_SLOTS, dtype=_F64, device=dev),
             info=torch.zeros(4, dtype=torch.int32, device=dev))
         self._ws = ws
         self._shared_len = _cabi.SHARED_HDR + N * K + N + self._TH
         dims = _cabi.Dims(R=R, N=N, K=K, Q=Q, KM=self._KM, MM=self._MM, PP=self._PP, TH=self._TH,
                           Mmax=max(self._M), n_ntiles=n_ntiles, S=self._S, reg=self._reg,
-                          desc_host=ctypes.cast(self._desc_host, ctypes.POINTER(_cabi.LatentDesc)))
+                          desc_host=ctypes.cast(self._desc_host, ctypes.POINTER(_cabi.LatentDesc)),
+                          spike_chunks=int(self._spike_chunks))
         self._dims = dims
         b = _cabi.Buffers()
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
@@ -353,30 +404,84 @@ class B200SVLowerBound:
             _cabi.check(_cabi.lib().svgpfa_elbo_grad(ctypes.byref(self._dims), ctypes.byref(b),
                                                      call_flags, self._stream()), "elbo_grad")
         self._kzz_key, self._spike_key = kz_key, sp_key
-        self._finish(shared)
+        self._finish(shared, flags)
         return shared, gZ, gm, gcv
 
-    def _finish(self, shared):
-        if self._pg is not None:
-            # the one exchange step of the path: [elbo.. | dC | dd | dtheta] summed over trial shards
+    # ------------------------------------------------------------------ exchange step and error channel
+    def _reduces(self, flags):
+        """Does this evaluation all-reduce the packed buffer?  """
+        if self._pg is None or self.shard_mode == "local":
+            return False
+        if self.shard_mode == "reduce":
+            return True
+        return sharding.evaluation_is_reduced(flags)
+
+    def _finish(self, shared, flags):
+        if self._reduces(flags):
+            # the one exchange step of the path: [elbo.., status | dC | dd | dtheta] summed over trial shards; the
+            # status travels in the header, so every rank sees a failed Cholesky of any shard and raises with it
             sharding.all_reduce_shared(shared, self._pg)
         if self._check_errors:
-            host = torch.cat([shared[:1], self._ws["info"].to(_F64)]).cpu()
-            if int(host[1]) == _cabi.INFO_NOT_PD:
+            self._enqueue_check(shared)
+
+    def _enqueue_check(self, shared):
+        """Asynchronous copy of the 8-double header [elbo, ell, kl, term1, term2, status, r, k] to pinned memory."""
+        if self._pinned is None:
+            self._pinned = torch.zeros(self._PENDING_SLOTS, _cabi.SHARED_HDR, dtype=_F64).pin_memory()
+            self._events = [torch.cuda.Event() for _ in range(self._PENDING_SLOTS)]
+        if len(self._pending) == self._PENDING_SLOTS:
+            self._poll_errors(block=True, limit=1)
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % self._PENDING_SLOTS
+        self._pinned[slot].copy_(shared[:_cabi.SHARED_HDR], non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(self._dev()))
+        self._pending.append(slot)
+
+    def _poll_errors(self, block, limit=None):
+        """Examines the header copies that have landed (all of them when ``block``)."""
+        done = 0
+        while self._pending and (limit is None or done < limit):
+            slot = self._pending[0]
+            ev = self._events[slot]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            self._pending.pop(0)
+            done += 1
+            hdr = self._pinned[slot]
+            if float(hdr[_cabi.SHARED_STATUS]) > 0.0:
+                self._pending.clear()
                 self._kzz_key = self._spike_key = None
-                raise torch.linalg.LinAlgError(
-                    f"linalg.cholesky: Kzz of trial {int(host[2])}, latent {int(host[3])} is not positive-definite")
-            if math.isinf(float(host[0])):
+                where = (f"Kzz of trial {int(hdr[6])}, latent {int(hdr[7])} is" if float(hdr[_cabi.SHARED_STATUS]) == 1.0
+                         else "a Kzz of more than one trial shard is")
+                raise torch.linalg.LinAlgError(f"linalg.cholesky: {where} not positive-definite")
+            if math.isinf(float(hdr[0])):
                 warnings.warn("infinity lower bound detected")       # svLowerBound.py:51-53
 
+    def checkErrors(self):
+        """Blocks until every evaluation issued so far has finished and raises what it reported."""
+        self._poll_errors(block=True)
+
     def _leaves(self):
-        return list(self._m) + list(self._cv) + [self._C, self._d] + list(self._theta) + list(self._Z)
+        return self._leaf_list
+
+    def _apply(self, cached_stats):
+        self._poll_errors(block=False)
+        leaves = self._leaf_list
+        differentiated = torch.is_grad_enabled() and any(p.requires_grad for p in leaves)
+        out = _LowerBoundFn.apply(self, cached_stats, *leaves)
+        if not differentiated:
+            # nobody will call backward(): the caller reads the value next, so report a failure here
+            # (reference semantics: the exception leaves the call that hit it)
+            self._poll_errors(block=True)
+        return out
 
     def eval(self):
         """ELL - KL as a 0-dim float64 tensor, differentiable w.r.t. every leaf that currently has
         ``requires_grad=True`` (svLowerBound.py:47-54)."""
         self._prepare()
-        return _LowerBoundFn.apply(self, None, *self._leaves())
+        return self._apply(None)
 
     # ------------------------------------------------------------------ host-buffer entry (bench.py "e2e")
     def makeHostIO(self, pin=True):
@@ -414,6 +519,10 @@ class B200SVLowerBound:
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().svgpfa_elbo_grad_host(ctypes.byref(self._dims), ctypes.byref(b), ctypes.byref(hio),
                                                           flags, self._stream()), "elbo_grad_host")
+            if self._pg is not None and self.shard_mode != "local":
+                # the one exchange step, on the device; the reduced buffer replaces the local one on the host
+                sharding.all_reduce_shared(shared, self._pg)
+                io["shared"].copy_(shared, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         self._kzz_key = self._spike_key = None
         nb = lambda *names: sum(io[n].numel() * io[n].element_size() for n in names)
@@ -425,7 +534,7 @@ class B200SVLowerBound:
             d2h += nb("gZ")
         if flags & _cabi.GRAD_POSTERIOR:
             d2h += nb("gm", "gcholvec")
-        if int(io["info"][0]) == _cabi.INFO_NOT_PD:
+        if int(io["info"][0]) == _cabi.INFO_NOT_PD or float(io["shared"][_cabi.SHARED_STATUS]) > 0.0:
             raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
         return float(io["shared"][0]), h2d, d2h
 
@@ -464,7 +573,7 @@ class B200SVLowerBound:
         self._prepare()
         if svPosteriorOnLatentsStats is None:
             svPosteriorOnLatentsStats = self.computeSVPosteriorOnLatentsStats()
-        return _LowerBoundFn.apply(self, svPosteriorOnLatentsStats, *self._leaves())
+        return self._apply(svPosteriorOnLatentsStats)
 
     def _run_cached(self, stats):
         dev = self._dev()
@@ -481,8 +590,7 @@ class B200SVLowerBound:
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().svgpfa_cached_ell_fwd_bwd(ctypes.byref(self._dims), ctypes.byref(b),
                                                               self._stream()), "cached_ell_fwd_bwd")
-        if self._pg is not None:
-            sharding.all_reduce_shared(shared, self._pg)
+        self._finish(shared, _cabi.GRAD_EMBEDDING)
         self._cached_keepalive = (mu_q, var_q, mu_s)
         return shared
 
@@ -522,30 +630,54 @@ class B200SVLowerBound:
         return [[cif[r, :, n] for n in range(cif.shape[2])] for r in range(cif.shape[0])]
 
     # ------------------------------------------------------------------ pickling (svEM.py:89-92,175-181)
+    # ``pickle`` does not preserve storage sharing between tensors (only torch.save does), so the leaf views -- and
+    # the kernel objects' parameter tensors, which alias the same packed buffer -- are NOT part of the state: they
+    # are rebuilt from the packed buffers on load, with their requires_grad flags.
+    _TRANSIENT = ("_bufs", "_dims", "_desc_host", "_desc_dev", "_ws", "_cached_keepalive", "_pg", "_Z", "_m", "_cv",
+                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared")
+
     def __getstate__(self):
-        st = dict(self.__dict__)
-        for key in ("_bufs", "_dims", "_desc_host", "_ws", "_cached_keepalive", "_pg"):
-            st.pop(key, None)
+        self._poll_errors(block=True)
+        st = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT}
         st["_ready"] = False
         st["_kzz_key"] = st["_spike_key"] = None
-        st["_desc_rows"] = [tuple(getattr(self._desc_host[k], f) for f, _ in _cabi.LatentDesc._fields_)
-                            for k in range(self._K)] if self._params_set else None
+        if self._params_set:
+            st["_leaf_requires_grad"] = [bool(p.requires_grad) for p in self._leaf_list]
+        if self._kernels is not None:
+            kernels = []
+            for kern in self._kernels:                 # kernel objects without their (aliasing) parameter tensor
+                kst = dict(kern.__dict__)
+                kst.pop("_params", None)
+                kernels.append((type(kern), kst))
+            st["_kernel_states"] = kernels
         return st
 
     def __setstate__(self, st):
-        rows = st.pop("_desc_rows", None)
+        flags = st.pop("_leaf_requires_grad", None)
+        kernels = st.pop("_kernel_states", None)
         self.__dict__.update(st)
         self._pg = None
         self._bufs = None
-        if rows is not None:
-            desc = (_cabi.LatentDesc * len(rows))()
-            for k, row in enumerate(rows):
-                desc[k] = _cabi.LatentDesc(*row)
-            self._desc_host = desc
+        self._pending, self._pinned, self._next_slot = [], None, 0
+        self._kernels = None
+        self._leaf_list = None
+        self._last_shared = None
+        if kernels is not None:
+            self._kernels = []
+            for cls, kst in kernels:
+                kern = cls.__new__(cls)
+                kern.__dict__.update(kst)
+                self._kernels.append(kern)
+        if self._params_set:
+            self._make_views()
+            self._bind_kernels()
+            self._refresh_leaf_list()
+            for p, flag in zip(self._leaf_list, flags or []):
+                p.requires_grad_(flag)
 
 
-def buildModelB200(kernels, device=None, process_group=None):
+def buildModelB200(kernels, device=None, process_group=None, shard_mode="auto"):
     """Sibling of ``SVGPFAModelFactory.buildModelPyTorch(kernels=...)`` for the in-scope model
     (point process, exponential link, linear embedding, Cholesky Kzz solves, Cholesky-vector
     covariance; stats/svGPFAModelFactory.py:40-148)."""
-    return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group)
+    return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group, shard_mode=shard_mode)

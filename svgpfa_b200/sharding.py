@@ -34,6 +34,34 @@ def trial_blocks(spikes_per_trial, world_size, per_spike_cost=1.0, per_trial_cos
     return [(int(cuts[i]), int(cuts[i + 1])) for i in range(world_size)]
 
 
+GRAD_POSTERIOR, GRAD_EMBEDDING, GRAD_KERNEL, GRAD_INDLOCS = 1, 2, 4, 8      # include/svgpfa_b200.h
+
+
+def evaluation_is_reduced(grad_flags):
+    """Whether an evaluation of a trial-sharded model all-reduces its packed buffer (``shard_mode="auto"``).
+
+    Given the shared parameters (C, d, theta) the bound is a sum of independent per-trial terms.  An optimiser over
+    SHARED leaves needs the global value and gradient at every closure call; all ranks receive bit-identical sums,
+    take identical decisions and stay in lock-step, so the all-reduce inside the evaluation is safe.  An optimiser
+    over PER-TRIAL leaves only (E-step: m, cholVecs; inducing-point M-step: Z) sees the other ranks' terms as
+    constants: each rank maximises its own block, with its own number of closure calls, so there must be NO
+    collective inside the evaluation (ranks would call it different numbers of times); the caller sums the final
+    bounds once per step (``svgpfa_b200.ecm``).  Evaluations that differentiate nothing, or both kinds of leaves
+    (one lock-step evaluation per rank, e.g. the benchmark's unit of work), are reduced."""
+    sharded = bool(grad_flags & (GRAD_POSTERIOR | GRAD_INDLOCS))
+    shared = bool(grad_flags & (GRAD_EMBEDDING | GRAD_KERNEL))
+    return shared or not sharded
+
+
+def trial_costs(spikes_per_trial, N, K, M, Q):
+    """Estimated cost of every trial, in nanoseconds on one B200, from the measured stage times of config #5
+    (profiles/README.md): the spike kernel is linear in spikes x (latent, inducing point) pairs, the quadrature,
+    embedding and inducing-point kernels cost the same for every trial."""
+    s = np.asarray(spikes_per_trial, dtype=np.float64)
+    per_trial = 0.9e-3 * K * Q * M * M + 0.6e-3 * Q * N * K + 1.8e-3 * K * M ** 3
+    return 1.03e-3 * s * K * M + per_trial
+
+
 def shared_layout(N, K, TH):
     """Offsets of the packed all-reduced buffer."""
     o_c = SHARED_HDR

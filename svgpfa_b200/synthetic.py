@@ -29,6 +29,8 @@ CONFIGS = {
     "config3": dict(R=2000,  N=200, K=10, M=20, Q=200, mixed=True,  ragged=False),
     "config4": dict(R=5000,  N=300, K=10, M=32, Q=200, mixed=False, ragged=True),
     "config5": dict(R=20000, N=500, K=20, M=32, Q=200, mixed=False, ragged=False),
+    # north_star "M up to 64": config #5's per-trial shape with 64 inducing points (the M > 32 kernels)
+    "m64":     dict(R=4000,  N=500, K=20, M=64, Q=200, mixed=False, ragged=False),
 }
 
 
@@ -169,17 +171,21 @@ def load_case(path):
     return case, extra
 
 
-def make_case_torch(cfg, device, *, seed=0, reg=1e-3, r0=0, r1=None, T=1.0):
-    """Device-side generator for the large benchmark workloads (same distributions as
-    ``make_case``; different random stream).  Generates trials [r0, r1) of the configuration so
-    that every rank of a trial-sharded run builds only its own shard; the shared parameters
-    (C, d, theta, per-neuron rates) depend on ``seed`` alone.  Returns a case dict of torch tensors
-    on ``device`` (spike_times float64 (S,), spike_counts int64 (R_local, N))."""
+GEN_BLOCK = 32        # trials per random-stream block of the device generator
+
+
+def _block_generator(device, seed, block, stream):
+    """One torch.Generator per (seed, block of GEN_BLOCK trials, stream): what a trial holds depends on
+    (seed, trial index) alone, never on how the trials are cut into shards."""
     import torch
-    cfg = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
-    R, N, K, M, Q = cfg["R"], cfg["N"], cfg["K"], cfg["M"], cfg["Q"]
-    r1 = R if r1 is None else r1
-    Rl = r1 - r0
+    gen = torch.Generator(device=device)
+    gen.manual_seed(((seed * 1000003 + block) * 4 + stream) * 2 + 1)
+    return gen
+
+
+def _shared_params(cfg, seed):
+    """(rate, C, d) -- the quantities every trial shares; functions of ``seed`` only."""
+    N, K = cfg["N"], cfg["K"]
     shared = np.random.default_rng(seed)
     if cfg["ragged"]:
         rate = np.exp(shared.uniform(np.log(1.0), np.log(200.0), size=N))
@@ -188,10 +194,75 @@ def make_case_torch(cfg, device, *, seed=0, reg=1e-3, r0=0, r1=None, T=1.0):
         rate = shared.uniform(5.0, 35.0, size=N)
         d = np.log(rate) + 0.1 * shared.standard_normal(N)
     C = 0.3 * shared.standard_normal((N, K))
+    return rate, C, d
+
+
+def _block_counts(cfg, device, seed, block, rate_t, T):
+    """Spike counts (rows, N) int64 of the trials of one generator block."""
+    import torch
+    rows = min(GEN_BLOCK, cfg["R"] - block * GEN_BLOCK)
+    gen = _block_generator(device, seed, block, 0)
     f64 = dict(dtype=torch.float64, device=device)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed * 1000003 + 17 * r0 + 1)
-    kernel_types, kernel_params, Z, m, chol_vecs = [], [], [], [], []
+    if cfg["ragged"]:
+        g_r = torch.exp(0.5 * torch.randn(rows, generator=gen, **f64))
+    else:
+        g_r = torch.ones(rows, **f64)
+    return torch.poisson(g_r[:, None] * rate_t[None, :] * T, generator=gen).to(torch.int64)
+
+
+def spike_counts_torch(cfg, device, *, seed=0, T=1.0):
+    """Spike counts (R, N) of EVERY trial of the configuration (cheap: no spike times), so that each rank of a
+    trial-sharded run can compute the same cost-balanced trial blocks before generating its own shard."""
+    import torch
+    cfg = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+    rate, _, _ = _shared_params(cfg, seed)
+    rate_t = torch.tensor(rate, dtype=torch.float64, device=device)
+    nblk = -(-cfg["R"] // GEN_BLOCK)
+    return torch.cat([_block_counts(cfg, device, seed, b, rate_t, T) for b in range(nblk)], 0)
+
+
+def make_case_torch(cfg, device, *, seed=0, reg=1e-3, r0=0, r1=None, T=1.0):
+    """Device-side generator for the large benchmark workloads (same distributions as ``make_case``;
+    different random stream).  Generates trials [r0, r1) of the configuration so that every rank of a
+    trial-sharded run builds only its own shard.  Random streams are drawn per block of GEN_BLOCK trials
+    from generators seeded by (seed, block index), so trial r holds the same numbers whatever the shard
+    boundaries are: an N-rank run evaluates exactly the data of the 1-rank run.  The shared parameters
+    (C, d, theta, per-neuron rates) depend on ``seed`` alone.  Returns a case dict of torch tensors on
+    ``device`` (spike_times float64 (S,), spike_counts int64 (R_local, N))."""
+    import torch
+    cfg = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+    R, N, K, M, Q = cfg["R"], cfg["N"], cfg["K"], cfg["M"], cfg["Q"]
+    r1 = R if r1 is None else r1
+    Rl = r1 - r0
+    rate, C, d = _shared_params(cfg, seed)
+    f64 = dict(dtype=torch.float64, device=device)
+    P = tril_size(M)
+    rows_i, cols_i = np.tril_indices(M)
+    diag = torch.tensor((rows_i == cols_i).astype(np.float64), **f64)
+    base = torch.linspace(0.0, T, M, **f64)
+    rate_t = torch.tensor(rate, **f64)
+    Zb, mb, cb, cnt_b, times_b = [], [], [], [], []
+    for b in range(r0 // GEN_BLOCK, -(-r1 // GEN_BLOCK) if Rl > 0 else r0 // GEN_BLOCK):
+        t0 = b * GEN_BLOCK
+        rows = min(GEN_BLOCK, R - t0)
+        lo, hi = max(r0, t0) - t0, min(r1, t0 + rows) - t0          # rows of the block inside [r0, r1)
+        gen = _block_generator(device, seed, b, 1)
+        jit = (torch.rand(rows, K, M, generator=gen, **f64) * 0.2 - 0.1) * T / M
+        Zb.append((base[None, None, :] + jit)[lo:hi])
+        mb.append(torch.randn(rows, K, M, generator=gen, **f64)[lo:hi])
+        cb.append((0.1 * diag[None, None, :] + 0.01 * torch.randn(rows, K, P, generator=gen, **f64))[lo:hi])
+        counts = _block_counts(cfg, device, seed, b, rate_t, T)
+        S = int(counts.sum().item())
+        seg = torch.repeat_interleave(torch.arange(rows * N, device=device), counts.reshape(-1), output_size=S)
+        gen_t = _block_generator(device, seed, b, 2)
+        key = seg.to(torch.float64) + torch.rand(S, generator=gen_t, **f64).clamp_(max=1.0 - 1e-9)
+        key, _ = torch.sort(key)
+        off = torch.cat([torch.zeros(1, dtype=torch.int64, device=device), counts.sum(1).cumsum(0)]).tolist()
+        times_b.append(((key - torch.floor(key)) * T)[off[lo]:off[hi]])
+        cnt_b.append(counts[lo:hi])
+    cat = lambda xs, shape: torch.cat(xs, 0) if xs else torch.zeros(shape, **f64)
+    Zall, mall, call = cat(Zb, (0, K, M)), cat(mb, (0, K, M)), cat(cb, (0, K, P))
+    kernel_types, kernel_params = [], []
     for k in range(K):
         if cfg["mixed"] and (k % 2 == 1):
             kernel_types.append("periodic")
@@ -199,29 +270,15 @@ def make_case_torch(cfg, device, *, seed=0, reg=1e-3, r0=0, r1=None, T=1.0):
         else:
             kernel_types.append("expquad")
             kernel_params.append(torch.tensor([0.1 + 0.05 * k], **f64))
-        base = torch.linspace(0.0, T, M, **f64)
-        jit = (torch.rand(Rl, M, generator=gen, **f64) * 0.2 - 0.1) * T / M
-        Z.append((base[None, :] + jit)[:, :, None].contiguous())
-        m.append(torch.randn(Rl, M, 1, generator=gen, **f64))
-        P = tril_size(M)
-        rows, cols = np.tril_indices(M)
-        diag = torch.tensor((rows == cols).astype(np.float64), **f64)
-        chol_vecs.append((0.1 * diag[None, :] + 0.01 * torch.randn(Rl, P, generator=gen, **f64))[:, :, None].contiguous())
+    Z = [Zall[:, k, :, None].contiguous() for k in range(K)]
+    m = [mall[:, k, :, None].contiguous() for k in range(K)]
+    chol_vecs = [call[:, k, :, None].contiguous() for k in range(K)]
+    del Zall, mall, call
     x, w = leg_quad(Q, 0.0, T)
     tq = torch.tensor(x, **f64)[None, :, None].repeat(Rl, 1, 1)
     wq = torch.tensor(w, **f64)[None, :, None].repeat(Rl, 1, 1)
-    rate_t = torch.tensor(rate, **f64)
-    if cfg["ragged"]:
-        g_r = torch.exp(0.5 * torch.randn(Rl, generator=gen, **f64))
-    else:
-        g_r = torch.ones(Rl, **f64)
-    counts = torch.poisson(g_r[:, None] * rate_t[None, :] * T, generator=gen).to(torch.int64)
-    S = int(counts.sum().item())
-    seg = torch.repeat_interleave(torch.arange(Rl * N, device=device), counts.reshape(-1), output_size=S)
-    key = seg.to(torch.float64) + torch.rand(S, generator=gen, **f64).clamp_(max=1.0 - 1e-9)
-    del seg
-    key, _ = torch.sort(key)
-    times = (key - torch.floor(key)) * T
+    counts = torch.cat(cnt_b, 0) if cnt_b else torch.zeros((0, N), dtype=torch.int64, device=device)
+    times = torch.cat(times_b) if times_b else torch.zeros(0, **f64)
     return dict(kernel_types=kernel_types, kernel_params=kernel_params, Z=Z, m=m, chol_vecs=chol_vecs,
                 C=torch.tensor(C, **f64), d=torch.tensor(d, **f64)[:, None].contiguous(),
                 leg_quad_points=tq, leg_quad_weights=wq, spike_times=times, spike_counts=counts,

@@ -21,13 +21,15 @@ def initial_params_from_case(case, device=None):
         "embedding": {"C0": t(case["C"]), "d0": t(case["d"])}}
 
 
-def model_from_case(case, device=None, process_group=None, nested=False, check_errors=True):
+def model_from_case(case, device=None, process_group=None, nested=False, check_errors=True, shard_mode="auto",
+                    spike_chunks=0):
     """A fully specified ``B200SVLowerBound`` for ``case``.  ``nested=True`` feeds the spikes
     through ``setMeasurements`` (nested python lists, the reference's format) instead of the
     flat fast path."""
     from .model import B200SVLowerBound
     model = B200SVLowerBound(kernels=build_kernels(case["kernel_types"]), device=device,
-                             process_group=process_group, check_errors=check_errors)
+                             process_group=process_group, check_errors=check_errors, shard_mode=shard_mode)
+    model._spike_chunks = spike_chunks
     model.setInitialParams(initial_params_from_case(case))
     if nested:
         model.setMeasurements(nested_spikes(case))

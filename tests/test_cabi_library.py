@@ -18,8 +18,8 @@ def lib():
     return _cabi.lib()
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "svgpfa_b200.h")).read()
+def _declared_symbols(header="svgpfa_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(r"\b(svgpfa_[a-z_0-9]+)\s*\(", text)))
 
 
@@ -30,6 +30,17 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _cabi.SYMBOLS, f"{name} has no ctypes signature"
     assert sorted(_cabi.SYMBOLS) == declared
+
+
+def test_probes_live_in_their_own_library(lib):
+    """Measurement probes and test hooks (include/svgpfa_b200_probes.h) are exported by the probes library and by
+    it alone: the product library carries no probe kernel."""
+    probes = _cabi.probes()
+    declared = _declared_symbols("svgpfa_b200_probes.h")
+    assert sorted(_cabi.PROBE_SYMBOLS) == declared
+    for name in declared:
+        assert hasattr(probes, name)
+        assert not hasattr(lib, name), f"{name} leaked into the product library"
 
 
 def test_abi_constants_match_header(lib):
@@ -45,7 +56,8 @@ def test_abi_constants_match_header(lib):
     fields = re.findall(r"\*\s*([A-Za-z_0-9]+);", body)
     assert tuple(fields) == _cabi.BUFFER_FIELDS
     assert ctypes.sizeof(_cabi.LatentDesc) == 32
-    assert ctypes.sizeof(_cabi.Dims) == 72
+    assert ctypes.sizeof(_cabi.Dims) == 80
+    assert get("SVGPFA_FIN_SLOTS") == _cabi.FIN_SLOTS
 
 
 def test_build_segments_host(lib):

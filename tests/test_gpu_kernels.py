@@ -17,7 +17,7 @@ def test_exp_neg_accuracy():
     """The library's exp for non-positive arguments vs numpy/libdevice exp down to exp(-706.9); below that
     (true value < 1e-306) it returns a value in [0, 1e-306]."""
     from svgpfa_b200 import _cabi
-    lib = _cabi.lib()
+    lib = _cabi.probes()
     dev = torch.device("cuda")
     gen = torch.Generator(device="cpu").manual_seed(0)
     x = torch.cat([-torch.rand(200000, generator=gen, dtype=torch.float64) * 40.0,
@@ -27,7 +27,7 @@ def test_exp_neg_accuracy():
                                 dtype=torch.float64)]).to(dev)
     yf, yr = torch.empty_like(x), torch.empty_like(x)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _cabi.check(lib.svgpfa_exp_neg_eval(x.data_ptr(), yf.data_ptr(), yr.data_ptr(), x.numel(), stream))
+    _cabi.check_probe(lib.svgpfa_exp_neg_eval(x.data_ptr(), yf.data_ptr(), yr.data_ptr(), x.numel(), stream))
     torch.cuda.synchronize()
     x, yf, yr = x.cpu().numpy(), yf.cpu().numpy(), yr.cpu().numpy()
     truth = np.exp(x)
@@ -49,7 +49,7 @@ def test_exp2m_accuracy():
     """The spike kernel's pre-scaled exponential 2^(-w2/256) vs numpy (long double) over its whole range;
     arguments above the limit are clamped (result ~6e-308 instead of 0 or a subnormal)."""
     from svgpfa_b200 import _cabi
-    lib = _cabi.lib()
+    lib = _cabi.probes()
     dev = torch.device("cuda")
     gen = torch.Generator(device="cpu").manual_seed(1)
     w2 = torch.cat([torch.rand(200000, generator=gen, dtype=torch.float64) * 400.0,
@@ -60,7 +60,7 @@ def test_exp2m_accuracy():
                                  dtype=torch.float64)]).to(dev)
     y = torch.empty_like(w2)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _cabi.check(lib.svgpfa_exp2m_eval(w2.data_ptr(), y.data_ptr(), w2.numel(), stream))
+    _cabi.check_probe(lib.svgpfa_exp2m_eval(w2.data_ptr(), y.data_ptr(), w2.numel(), stream))
     torch.cuda.synchronize()
     w2, y = w2.cpu().numpy(), y.cpu().numpy()
     inside = w2 <= 2.609e5

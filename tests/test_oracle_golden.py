@@ -18,6 +18,17 @@ from svgpfa_b200 import synthetic
 GRAD_KEYS = ("grad_C", "grad_d")
 
 
+@pytest.fixture(autouse=True)
+def _fixture_thread_count():
+    """The fixtures were produced with 8 BLAS threads (tests/golden/make_golden.py); the reference's own gradients
+    move in the 11th digit with the thread count, and other test modules lower it."""
+    import torch
+    before = torch.get_num_threads()
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    yield
+    torch.set_num_threads(before)
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_oracle_matches_reference(name):
     case, ref = synthetic.load_case(os.path.join(GOLDEN, name + ".npz"))
@@ -30,8 +41,11 @@ def test_oracle_matches_reference(name):
     keys = list(GRAD_KEYS)
     for k in range(K):
         keys += [f"grad_m_{k}", f"grad_chol_vecs_{k}", f"grad_kernel_params_{k}", f"grad_Z_{k}"]
+    # config1_example holds 197 662 spikes and Kzz with long length scales: the reference's own gradients move by
+    # 3e-11 with the number of BLAS threads (fixture: 8 threads; measured with 1 thread: 3.1e-11 on grad_Z)
+    tol = 1e-10 if name == "config1_example" else 1e-11
     for key in keys:
-        assert rel_err(out[key], ref[key]) <= 1e-11, key
+        assert rel_err(out[key], ref[key]) <= tol, key
     if with_stats:
         for key in ("quad_latent_mean", "quad_latent_var", "spike_latent_mean", "spike_latent_var",
                     "quad_embedding_mean", "quad_embedding_var", "spike_embedding_mean"):

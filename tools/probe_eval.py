@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from svgpfa_b200 import _cabi
 
-lib = _cabi.lib()
+lib = _cabi.probes()
 dev = torch.device("cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 names = {20: "full", 21: "no moments", 22: "no table LDS", 23: "no spike-time LDS"}
@@ -22,7 +22,7 @@ for per_sm in (5, 3, 2, 1):
         for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _cabi.check(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), st))
+            _cabi.check_probe(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), st))
             e1.record()
             e1.synchronize()
             best = min(best, e0.elapsed_time(e1))

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from svgpfa_b200 import _cabi
 
-lib = _cabi.lib()
+lib = _cabi.probes()
 dev = torch.device("cuda")
 blocks = 148 * 8
 out = torch.zeros(blocks * 256, dtype=torch.float64, device=dev)
@@ -23,7 +23,7 @@ for kind in (0, 10, 11, 12, 13, 14, 15, 16, 3):
         out.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _cabi.check(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), st))
+        _cabi.check_probe(lib.svgpfa_peak_probe(kind, blocks, iters, out.data_ptr(), st))
         e1.record()
         e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
