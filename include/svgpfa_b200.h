@@ -85,7 +85,8 @@ typedef struct svgpfa_dims {
                                      entry uses the range to pipeline copies and kernels over blocks of trials. */
     int32_t spike_chunks;         /* tuning: neuron ranges per trial in the spike kernel's grid; 0 = automatic
                                      (tests force 1: whole-trial ranges, several spike tiles per CTA) */
-    int32_t reserved0;
+    int32_t quad_warps;           /* tuning: warps per CTA of the M <= 32 quadrature kernels (one 32-point tile per warp
+                                     and pass); 0 = automatic (min(ceil(Q/32), 7)) */
 } svgpfa_dims;
 
 #define SVGPFA_NTRIALS(d) ((d)->rn ? (d)->rn : (d)->R)

@@ -33,7 +33,7 @@ class LatentDesc(C.Structure):
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("R", "N", "K", "Q", "KM", "MM", "PP", "TH", "Mmax", "n_ntiles")] + [
         ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc)), ("r0", C.c_int32), ("rn", C.c_int32),
-        ("spike_chunks", C.c_int32), ("reserved0", C.c_int32)]
+        ("spike_chunks", C.c_int32), ("quad_warps", C.c_int32)]
 
 
 BUFFER_FIELDS = (

@@ -106,38 +106,59 @@ __device__ __forceinline__ void svgpfa_pin(double (&x)[NE]) {
     else asm volatile("" : "+d"(x[0]));
 }
 
-template <int NE>
+// VAR (bit mask, measured with tools/probe_eval.py):
+//   1  degree-3 polynomial instead of degree 4: the Taylor series of exp(-y), |y| <= h = ln2/512, truncated after y^4
+//      with y^4 replaced by its best quadratic on [-h, h] (Chebyshev economisation: y^4 ~ h^2 y^2 - h^4/8), i.e.
+//      exp(-y) ~ (1 - h^4/192) - y + (1/2 + h^2/24) y^2 - y^3/6, maximum relative error 1.8e-14 -- four orders inside
+//      BASELINE.json's 1e-10 -- and one FP64 instruction fewer per evaluation;
+//   2  the rounded integer comes back through the conversion unit (I2F.F64.S32 of the low word of MAGIC - w2)
+//      instead of a second FP64 subtraction: one more FP64 issue slot moved off the FP64 pipe.
+template <int NE, int VAR = 0>
 __device__ __forceinline__ void svgpfa_exp2m_n(const double (&w2)[NE], unsigned lane_tab, double (&out)[NE]) {
     const double MAGIC = 6755399441055744.0;
-    const double L = SVGPFA_EXP2M_L;
+    const double L = SVGPFA_EXP2M_L, H = 0.5 * SVGPFA_EXP2M_L;
     const double C1 = L, C2 = L * L / 2.0, C3 = L * L * L / 6.0, C4 = L * L * L * L / 24.0;
+    const double E0 = 1.0 - H * H * H * H / 192.0, E2 = L * L * (0.5 + H * H / 24.0);
     double t[NE], u[NE], q[NE], T[NE];
+    int n[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) t[e] = MAGIC - w2[e];
     svgpfa_pin(t);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const int n = __double2loint(t[e]);
+        n[e] = __double2loint(t[e]);
         double Tb;
         asm("{\n\t.reg .u32 i, a;\n\tand.b32 i, %1, 255;\n\tmad.lo.u32 a, i, 128, %2;\n\tld.shared.f64 %0, [a];\n\t}"
-            : "=d"(Tb) : "r"(n), "r"(lane_tab));
-        T[e] = __hiloint2double(__double2hiint(Tb) + (n << (20 - SVGPFA_EXP2M_BITS)), __double2loint(Tb));
+            : "=d"(Tb) : "r"(n[e]), "r"(lane_tab));
+        T[e] = __hiloint2double(__double2hiint(Tb) + (n[e] << (20 - SVGPFA_EXP2M_BITS)), __double2loint(Tb));
     }
 #pragma unroll
-    for (int e = 0; e < NE; ++e) u[e] = w2[e] + (t[e] - MAGIC);
+    for (int e = 0; e < NE; ++e) u[e] = w2[e] + ((VAR & 2) ? __int2double_rn(n[e]) : (t[e] - MAGIC));
     svgpfa_pin(u);
+    if (VAR & 1) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) q[e] = fma(u[e], C4, -C3);
-    svgpfa_pin(q);
+        for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], C3, E2);
+        svgpfa_pin(q);
 #pragma unroll
-    for (int e = 0; e < NE; ++e) q[e] = fma(u[e], q[e], C2);
-    svgpfa_pin(q);
+        for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], C1);
+        svgpfa_pin(q);
 #pragma unroll
-    for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], C1);
-    svgpfa_pin(q);
+        for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], E0);
+        svgpfa_pin(q);
+    } else {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], 1.0);
-    svgpfa_pin(q);
+        for (int e = 0; e < NE; ++e) q[e] = fma(u[e], C4, -C3);
+        svgpfa_pin(q);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[e] = fma(u[e], q[e], C2);
+        svgpfa_pin(q);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], C1);
+        svgpfa_pin(q);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[e] = fma(-u[e], q[e], 1.0);
+        svgpfa_pin(q);
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) out[e] = T[e] * q[e];
     svgpfa_pin(out);
@@ -287,6 +308,116 @@ __device__ __forceinline__ void kappa_grad_t(const KConst& kc, double delta, con
         dk_dt0 = kv * q * kc.dl;
         dk_dt1 = kv * s2x * delta * kc.dp;
     }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// NE independent kernel evaluations written stage by stage (the quadrature kernels' element-wise phases).
+// Why: with two resident warps per scheduler these phases are latency-bound -- ptxas emits the evaluations of an
+// unrolled loop one dependency chain after the other, and a chain is ~14 dependent FP64 instructions of ~10 cycles
+// (ncu: "wait" was the top stall of both quadrature kernels).  The opaque pins keep NE chains in flight.
+// --------------------------------------------------------------------------------------------------------------
+// exp(x) for x <= 0, 64-entry table in shared memory (svgpfa_load_exp_tab64), same arithmetic as svgpfa_exp_neg64
+template <int NE>
+__device__ __forceinline__ void svgpfa_exp_neg64_n(double (&x)[NE], const double* __restrict__ tab, double (&out)[NE]) {
+    const double MAGIC = 6755399441055744.0;
+    double t[NE], r[NE], q[NE], T[NE];
+    int n[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const unsigned hi = min((unsigned)__double2hiint(x[e]), 0xC08617FFu);          // clamp to > -707
+        x[e] = __hiloint2double((int)hi, __double2loint(x[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) t[e] = fma(x[e], SVGPFA_EXP_INV_L * 0.03125, MAGIC);   // 64 / ln2
+    svgpfa_pin(t);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        n[e] = __double2loint(t[e]);
+        T[e] = tab[n[e] & 63];
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) r[e] = fma(t[e] - MAGIC, -32.0 * SVGPFA_EXP_L, x[e]);  // |r| <= ln2 / 128
+    svgpfa_pin(r);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(r[e], 1.0 / 120.0, 1.0 / 24.0);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(q[e], r[e], 1.0 / 6.0);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(q[e], r[e], 0.5);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) q[e] = fma(q[e], r[e], 1.0);
+    svgpfa_pin(q);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const double v = fma(T[e] * r[e], q[e], T[e]);
+        out[e] = __hiloint2double(__double2hiint(v) + ((n[e] >> 6) << 20), __double2loint(v));
+    }
+}
+
+// sin and cos of 2 pi x by table (x64 = 64 x): n = rint(64 x), u = 64 x - n in [-1/2, 1/2], theta = 2 pi u / 64,
+//   sin(2 pi x) = S_n cos(theta) + C_n sin(theta),  cos(2 pi x) = C_n cos(theta) - S_n sin(theta)
+// with (S_n, C_n) = sincos(2 pi n / 64) in shared memory and Taylor polynomials of degree 7 / 8 in theta (|theta| <=
+// 0.0491: truncation < 5e-18).  19 FP64 instructions against ~40 (+ ~20 others and branches) of libdevice's sincospi.
+// `tab` points at this lane's replica of entry 0; consecutive entries are STRIDE double2 apart (the spike kernel
+// replicates the table 16 times to keep the gathers conflict-free; the quadrature kernels use one copy).
+#define SVGPFA_SC_ENTRIES 64
+
+template <int STRIDE>
+__device__ __forceinline__ void svgpfa_load_sincos_tab(double2* tab) {
+    for (int i = threadIdx.x; i < SVGPFA_SC_ENTRIES * STRIDE; i += blockDim.x) {
+        double sv, cv;
+        sincospi((double)(i / STRIDE) * (2.0 / SVGPFA_SC_ENTRIES), &sv, &cv);
+        tab[i] = make_double2(sv, cv);
+    }
+}
+
+template <int STRIDE>
+__device__ __forceinline__ void svgpfa_sincos2pi_tab(double x64, const double2* __restrict__ tab, double& sv, double& cv) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double t = x64 + MAGIC;
+    const double u = x64 - (t - MAGIC);
+    const int n = __double2loint(t) & (SVGPFA_SC_ENTRIES - 1);
+    const double th = u * (2.0 * SVGPFA_PI / SVGPFA_SC_ENTRIES), th2 = th * th;
+    double ps = fma(th2, -1.0 / 5040.0, 1.0 / 120.0);
+    ps = fma(th2, ps, -1.0 / 6.0);
+    const double st = fma(th * th2, ps, th);                  // sin(theta)
+    double pc = fma(th2, 1.0 / 40320.0, -1.0 / 720.0);
+    pc = fma(th2, pc, 1.0 / 24.0);
+    pc = fma(th2, pc, -0.5);
+    const double ct = fma(th2, pc, 1.0);                      // cos(theta)
+    const double2 sc = tab[n * STRIDE];
+    sv = fma(sc.x, ct, sc.y * st);
+    cv = fma(sc.y, ct, -sc.x * st);
+}
+
+// kappa(delta_e), e < NE, for one latent.  etab: 64-entry exp table, sctab: single-copy sincos table (periodic only).
+// Periodic: sin^2(pi d/p) = (1 - cos(2 pi d/p)) / 2; q[e] returns that square (expquad: delta^2) and s2x[e] the
+// sine of the doubled angle (expquad: unused) for the derivative formulas of kappa_grad.
+template <int NE>
+__device__ __forceinline__ void kappa_vals_n(const KConst& kc, const double (&delta)[NE], const double* __restrict__ etab,
+                                             const double2* __restrict__ sctab, double (&kv)[NE], double (&q)[NE],
+                                             double (&s2x)[NE]) {
+    double x[NE];
+    if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) q[e] = delta[e] * delta[e];
+    } else {
+        const double invp64 = kc.invp * SVGPFA_SC_ENTRIES;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            double c2x;
+            svgpfa_sincos2pi_tab<1>(delta[e] * invp64, sctab, s2x[e], c2x);
+            q[e] = fmax(0.5 * (1.0 - c2x), 0.0);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) x[e] = kc.nh * q[e];
+    svgpfa_exp_neg64_n<NE>(x, etab, kv);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) kv[e] *= kc.s2;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(256) issue_probe_kernel(long iters, double* ou
 
 // The spike kernel's evaluation sequence in isolation (no segments, no staging): per step 4 evaluations of
 // w = t sc + zs, kappa = 2^(-w^2/256), pn += kappa, p1 += kappa w, p2 += kappa w^2 with t read from shared memory.
-// MODE 0: as in the kernel; 1: without the moment accumulations (KGRAD = false); 2: table entry replaced by a constant
-// (no table LDS); 3: without the spike-time LDS.
+// MODE 0: as in the round-1 kernel; 1: without the moment accumulations (KGRAD = false); 2: table entry replaced by a
+// constant (no table LDS); 3: without the spike-time LDS; 4: degree-3 polynomial; 5: I2F range reduction; 6: both;
+// 7: both + pre-scaled spike times (w = ts + zs: a two-register DADD instead of a three-register DFMA).
 template <int MODE>
 __global__ void __maxnreg__(128) eval_probe_kernel(long iters, double* out) {
     __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
@@ -96,7 +97,7 @@ __global__ void __maxnreg__(128) eval_probe_kernel(long iters, double* out) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) t[e] = MODE == 3 ? 1e-3 * e + pn * 1e-300 : tp[e];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { w[e] = fma(t[e], sc, zs); w2[e] = w[e] * w[e]; }
+        for (int e = 0; e < 4; ++e) { w[e] = MODE == 7 ? t[e] + zs : fma(t[e], sc, zs); w2[e] = w[e] * w[e]; }
         if (MODE == 2) {
             const double MAGIC = 6755399441055744.0, L = SVGPFA_EXP2M_L;
 #pragma unroll
@@ -110,6 +111,12 @@ __global__ void __maxnreg__(128) eval_probe_kernel(long iters, double* out) {
                 const double T = __hiloint2double(0x3ff00000 + (n << 12), n & 255);
                 kv[e] = fma(-(T * u), q, T);
             }
+        } else if (MODE == 4) {
+            svgpfa_exp2m_n<4, 1>(w2, lane_tab, kv);
+        } else if (MODE == 5) {
+            svgpfa_exp2m_n<4, 2>(w2, lane_tab, kv);
+        } else if (MODE == 6 || MODE == 7) {
+            svgpfa_exp2m_n<4, 3>(w2, lane_tab, kv);
         } else {
             svgpfa_exp2m_n<4>(w2, lane_tab, kv);
         }
@@ -213,6 +220,10 @@ extern "C" int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, do
         case 21: eval_probe_kernel<1><<<blocks, 128, 0, st>>>((long)iters, out); break;
         case 22: eval_probe_kernel<2><<<blocks, 128, 0, st>>>((long)iters, out); break;
         case 23: eval_probe_kernel<3><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 24: eval_probe_kernel<4><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 25: eval_probe_kernel<5><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 26: eval_probe_kernel<6><<<blocks, 128, 0, st>>>((long)iters, out); break;
+        case 27: eval_probe_kernel<7><<<blocks, 128, 0, st>>>((long)iters, out); break;
         default: return probe_error("peak_probe kind", cudaSuccess);
     }
     { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return probe_error("peak_probe", e_); }

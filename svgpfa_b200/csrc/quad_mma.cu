@@ -16,7 +16,8 @@
 
 namespace {
 
-constexpr int QM_WARPS = 4;
+constexpr int QM_MAX_WARPS = 4;               // measured on the 2000-trial shard: 7 warps (Q = 200: one 32-point tile per warp, one pass,
+                                              // one CTA per SM in the adjoint) 4.76 ms against 3.87 ms for 4 warps (two CTAs per SM)
 constexpr int QM_LDT = 36;                    // leading dimension of the per-warp 32-point tiles
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -31,15 +32,20 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 }
 
 // Element-wise work (kernel evaluations, their derivatives, row sums) is written as ROLLED loops over a shared
-// tile with lane <-> point or lane <-> inducing point; only the mma sequences are unrolled.  (A first version kept
-// the kernel values in fragment registers and unrolled everything: 10 500 instructions, 23 % of the stall samples
-// were instruction-cache misses -- profiles/README.md.)
+// tile with lane <-> point or lane <-> inducing point, four independent evaluations per iteration (kappa_vals_n:
+// the dependency chains are interleaved stage by stage); only the mma sequences are unrolled.  History
+// (profiles/README.md): a first version kept the kernel values in fragment registers and unrolled everything
+// (10 500 instructions, 23 % instruction-cache stalls); the round-1 forward kernel still generated K in B-fragment
+// registers (32 inlined evaluations per pass: 16 % instruction-fetch stalls, 166 registers) and both kernels ran
+// one evaluation chain at a time ("wait" was the top stall with two resident warps per scheduler).
 template <int MT, bool BWD>
-__global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+__global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 2 : 4)
+quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     __shared__ double etab[64];
+    __shared__ double2 sctab[SVGPFA_SC_ENTRIES];
     svgpfa_load_exp_tab64(etab);
     const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
     const svgpfa_latent_desc ds = bf.desc[k];
@@ -53,12 +59,14 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
     double* zs = al + MP;                               // [MP]
     constexpr int WSTRIDE = (BWD ? 2 : 1) * MP * LDT + 3 * 32;
     double* wbase = zs + MP + (size_t)warp * WSTRIDE;
-    double* tileV = wbase;                              // [MP][LDT]  V, later Li^T W
-    double* tileU = wbase + MP * LDT;                   // [MP][LDT]  K, later U, later W      (BWD only)
+    double* tileV = wbase;                              // [MP][LDT]  (FWD: K, then) V, later Li^T W
+    double* tileU = wbase + (BWD ? MP * LDT : 0);       // [MP][LDT]  K, later U, later W      (BWD only)
+    double* tileK = BWD ? tileU : tileV;
     double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the tile
     double* mbs = tt + 32;                              // [32] mubar
-    double* vbs = mbs + 32;                             // [32] varbar
+    double* vbs = mbs + 32;                             // [32] 2 varbar
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+    if (kc.type == SVGPFA_KERNEL_PERIODIC) svgpfa_load_sincos_tab<1>(sctab);
     {
         const size_t mo = (size_t)r * dm.MM + ds.mmoff;
         // Li and X are first needed by the V product, after the kernel evaluations of the first pass: when the rows
@@ -90,12 +98,12 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
         }
     }
     __syncthreads();
-    // persistent accumulators of the adjoint (BWD); lane j owns abar_j, dz_j
+    // persistent accumulators of the adjoint (BWD); lane j owns abar_j and the raw moments of dz_j, dtheta
     constexpr int NTA = MT * (MT + 1) / 2;
     double accA[BWD ? NTA : 1][2];
 #pragma unroll
     for (int e = 0; e < (BWD ? NTA : 1); ++e) accA[e][0] = accA[e][1] = 0.0;
-    double ab_own = 0.0, dz_own = 0.0, th0 = 0.0, th1 = 0.0;
+    double ab_own = 0.0, dz_raw = 0.0, th0_raw = 0.0, th1_raw = 0.0;
     const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
     const int ntq = (dm.Q + 31) / 32;
@@ -113,15 +121,23 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(bf.varbar_part + p * part_stride + o));
             }
         }
-        // ---- kernel values.  BWD: lane <-> point, K[j][q] -> tileU (rolled loop; the tile feeds abar and the V
-        //      product).  FWD: directly in B-fragment registers kf[ks][qt] = kappa(t[8 qt + g] - z[4 ks + tg]) --
-        //      one tile less of shared memory, three resident CTAs per SM instead of two (measured 2.1 vs 2.8 ms).
-        double kf[BWD ? 1 : KS][4];
-        double mu4[4] = {0.0, 0.0, 0.0, 0.0};
+        // ---- kernel values K[j][q], lane <-> point, four inducing points per iteration -> tileK.
+        //      FWD: mu_q = k_q . alpha falls out of the same loop without any cross-lane reduction.
+        double mu_lane = 0.0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < MP; j0 += 4) {
+            double dl[4], kv[4], qq[4], s2x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dl[e] = t_lane - zs[j0 + e];
+            kappa_vals_n<4>(kc, dl, etab, sctab, kv, qq, s2x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double v = (valid && j0 + e < M) ? kv[e] : 0.0;
+                tileK[(j0 + e) * LDT + lane] = v;
+                if (!BWD) mu_lane = fma(v, al[j0 + e], mu_lane);
+            }
+        }
         if (BWD) {
-#pragma unroll 2
-            for (int j = 0; j < MP; ++j)
-                tileU[j * LDT + lane] = (valid && j < M) ? kappa_val_t(kc, t_lane - zs[j], etab) : 0.0;
             double mbar = 0.0, vbar = 0.0;
             if (valid) {
                 const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;
@@ -132,33 +148,22 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
             }
             mbs[lane] = mbar;
             vbs[lane] = vbar;
-        } else {
-            __syncwarp();                                            // tt visible
-            double t4[4];
-            bool v4[4];
-#pragma unroll
-            for (int qt = 0; qt < 4; ++qt) { t4[qt] = tt[8 * qt + g]; v4[qt] = (qbase + 8 * qt + g) < dm.Q; }
-#pragma unroll
-            for (int ks = 0; ks < (BWD ? 1 : KS); ++ks) {
-                const int j = 4 * ks + tg;
-                const double zj = zs[j], aj = al[j];
-#pragma unroll
-                for (int qt = 0; qt < 4; ++qt) {
-                    kf[ks][qt] = (v4[qt] && j < M) ? kappa_val_t(kc, t4[qt] - zj, etab) : 0.0;
-                    mu4[qt] = fma(kf[ks][qt], aj, mu4[qt]);
-                }
-            }
+        } else if (valid) {
+            bf.mu_q[((size_t)r * dm.Q + q_lane) * dm.K + k] = mu_lane;
         }
         __syncwarp();
         if (BWD && lane < MP) {
             // abar_j += sum_q mubar_q K[j][q], lane <-> inducing point, skewed column order (conflict free)
-            double s_ = 0.0;
-#pragma unroll 4
-            for (int c = 0; c < 32; ++c) {
-                const int q = (c + lane) & 31;
-                s_ = fma(mbs[q], tileU[lane * LDT + q], s_);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+            for (int c = 0; c < 32; c += 4) {
+                const int q0 = (c + lane) & 31, q1 = (c + 1 + lane) & 31, q2 = (c + 2 + lane) & 31, q3 = (c + 3 + lane) & 31;
+                s0 = fma(mbs[q0], tileU[lane * LDT + q0], s0);
+                s1 = fma(mbs[q1], tileU[lane * LDT + q1], s1);
+                s2 = fma(mbs[q2], tileU[lane * LDT + q2], s2);
+                s3 = fma(mbs[q3], tileU[lane * LDT + q3], s3);
             }
-            ab_own += s_;
+            ab_own += (s0 + s1) + (s2 + s3);
         }
         if (first_pass) {                         // Li, X of the cp.async staging become visible to the whole CTA
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
         for (int ks = 0; ks < KS; ++ks) {
             double b[4];
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) b[qt] = BWD ? tileU[(4 * ks + tg) * LDT + 8 * qt + g] : kf[BWD ? 0 : ks][qt];
+            for (int qt = 0; qt < 4; ++qt) b[qt] = tileK[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
             for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
                 const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
@@ -194,6 +199,7 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                     vv[qt][1] = fma(v[rt][qt][1], v[rt][qt][1], vv[qt][1]);
                 }
             }
+            __syncwarp();                                            // every lane is done reading K (same tile)
         }
 #pragma unroll
         for (int rt = 0; rt < MT; ++rt)
@@ -241,14 +247,6 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                     if (q < dm.Q) bf.var_q[((size_t)r * dm.Q + q) * dm.K + k] = kc.s2 + d0;
                     if (q + 1 < dm.Q) bf.var_q[((size_t)r * dm.Q + q + 1) * dm.K + k] = kc.s2 + d1;
                 }
-            }
-#pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {                       // mu = k . alpha: sum over the 4 k groups
-                double m = mu4[qt];
-                m += __shfl_xor_sync(0xffffffffu, m, 1);
-                m += __shfl_xor_sync(0xffffffffu, m, 2);
-                const int q = qbase + 8 * qt + g;
-                if (tg == 0 && q < dm.Q) bf.mu_q[((size_t)r * dm.Q + q) * dm.K + k] = m;
             }
         } else {
             // ---- A += V diag(varbar) V^T over the 32 points: k-step = 4 points, A/B fragments from the V tile
@@ -325,17 +323,34 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
                     for (int qt = 0; qt < 4; ++qt)
                         *reinterpret_cast<double2*>(tileV + (8 * jt + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[jt][qt][0], w[jt][qt][1]);
                 __syncwarp();
-                // ---- kbar = 2 varbar Kv + mubar alpha and its products with dkappa; lane <-> inducing point
+                // ---- kbar = 2 varbar Kv + mubar alpha and its products with dkappa; lane <-> inducing point, four
+                //      points per iteration.  Raw moments only: h = kbar kappa, dz += h (delta | sin 2x),
+                //      th0 += h (delta^2 | sin^2), th1 += h sin 2x delta; the constants dd, dl, dp are applied once.
                 if (lane < M) {
-#pragma unroll 2
-                    for (int c = 0; c < 32; ++c) {
-                        const int q = (c + lane) & 31;
-                        const double kbar = 2.0 * vbs[q] * tileV[lane * LDT + q] + mbs[q] * aj_own;
-                        double kval, dkd, d0, d1;
-                        kappa_grad_t(kc, tt[q] - zj_own, etab, kval, dkd, d0, d1);
-                        dz_own = fma(-kbar, dkd, dz_own);            // d delta / d z = -1
-                        th0 = fma(kbar, d0, th0);
-                        th1 = fma(kbar, d1, th1);
+#pragma unroll 1
+                    for (int c = 0; c < 32; c += 4) {
+                        double dl[4], kv[4], qq[4], s2x[4];
+                        int qi[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            qi[e] = (c + e + lane) & 31;
+                            dl[e] = tt[qi[e]] - zj_own;
+                        }
+                        kappa_vals_n<4>(kc, dl, etab, sctab, kv, qq, s2x);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double kbar = fma(2.0 * vbs[qi[e]], tileV[lane * LDT + qi[e]], mbs[qi[e]] * aj_own);
+                            const double h = kbar * kv[e];
+                            if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+                                dz_raw = fma(h, dl[e], dz_raw);
+                                th0_raw = fma(h, qq[e], th0_raw);
+                            } else {
+                                const double hs = h * s2x[e];
+                                dz_raw += hs;
+                                th0_raw = fma(h, qq[e], th0_raw);
+                                th1_raw = fma(hs, dl[e], th1_raw);
+                            }
+                        }
                     }
                 }
             }
@@ -343,6 +358,9 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
         __syncwarp();                                                // tiles are reused by the next pass
     }
     if (!BWD) return;
+    // d delta / d z = -1;  dkappa/ddelta = kappa (delta | sin 2x) dd,  dkappa/dtheta0 = kappa (delta^2 | sin^2) dl,
+    // dkappa/dtheta1 = kappa sin 2x delta dp  (kappa_grad in common.cuh); kappa's scale^2 is inside kv
+    const double dz_own = -kc.dd * dz_raw, th0 = kc.dl * th0_raw, th1 = kc.dp * th1_raw;
     // ---- combine the warps through their (now idle) V tiles
     __syncthreads();
 #pragma unroll
@@ -393,10 +411,12 @@ __global__ void __launch_bounds__(32 * QM_WARPS) quad_latent_mma_kernel(svgpfa_d
 template <int MT, bool BWD>
 void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
     int nw = (dims->Q + 31) / 32;
-    if (nw > QM_WARPS) nw = QM_WARPS;
+    int cap = dims->quad_warps > 0 ? dims->quad_warps : QM_MAX_WARPS;
+    if (cap > QM_MAX_WARPS) cap = QM_MAX_WARPS;
+    if (nw > cap) nw = cap;
     if (nw < 1) nw = 1;
     const size_t smem = sizeof(double) * qm_smem_doubles(8 * MT, nw, BWD);
-    SVGPFA_ENSURE_SMEM(smem, quad_latent_mma_kernel<MT, BWD>);
+    SVGPFA_ENSURE_SMEM(sizeof(double) * qm_smem_doubles(8 * MT, QM_MAX_WARPS, BWD), quad_latent_mma_kernel<MT, BWD>);
     quad_latent_mma_kernel<MT, BWD><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
 }
 

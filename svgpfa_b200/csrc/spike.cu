@@ -198,33 +198,13 @@ __device__ __forceinline__ void eq_run(const double* __restrict__ tp, int cnt, d
 // with (S_n, C_n) = sincos(2 pi n / 64) in shared memory (64 entries x 16 replicas, conflict-free like the exp table) and
 // Taylor polynomials of degree 7 / 8 in theta (truncation < 5e-18).  19 FP64 instructions against ~40 (+ ~20 others) of
 // libdevice's sincospi, which computes a full-range sine AND cosine polynomial.
-constexpr int ST_SC_ENTRIES = 64;
+constexpr int ST_SC_ENTRIES = SVGPFA_SC_ENTRIES;
 constexpr int ST_SC_DOUBLES = 2 * ST_SC_ENTRIES * SVGPFA_EXP2M_REP;        // 16 KB
 
-__device__ __forceinline__ void load_sincos_tab(double2* tab) {
-    for (int i = threadIdx.x; i < ST_SC_ENTRIES * SVGPFA_EXP2M_REP; i += blockDim.x) {
-        double sv, cv;
-        sincospi((double)(i / SVGPFA_EXP2M_REP) * (2.0 / ST_SC_ENTRIES), &sv, &cv);
-        tab[i] = make_double2(sv, cv);
-    }
-}
+__device__ __forceinline__ void load_sincos_tab(double2* tab) { svgpfa_load_sincos_tab<SVGPFA_EXP2M_REP>(tab); }
 
 __device__ __forceinline__ void sincos2pi_tab(double x64, const double2* __restrict__ lane_sc, double& sv, double& cv) {
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
-    const double t = x64 + MAGIC;
-    const double u = x64 - (t - MAGIC);
-    const int n = __double2loint(t) & (ST_SC_ENTRIES - 1);
-    const double th = u * (2.0 * SVGPFA_PI / ST_SC_ENTRIES), th2 = th * th;
-    double ps = fma(th2, -1.0 / 5040.0, 1.0 / 120.0);
-    ps = fma(th2, ps, -1.0 / 6.0);
-    const double st = fma(th * th2, ps, th);                  // sin(theta)
-    double pc = fma(th2, 1.0 / 40320.0, -1.0 / 720.0);
-    pc = fma(th2, pc, 1.0 / 24.0);
-    pc = fma(th2, pc, -0.5);
-    const double ct = fma(th2, pc, 1.0);                      // cos(theta)
-    const double2 sc = lane_sc[n * SVGPFA_EXP2M_REP];
-    sv = fma(sc.x, ct, sc.y * st);
-    cv = fma(sc.y, ct, -sc.x * st);
+    svgpfa_sincos2pi_tab<SVGPFA_EXP2M_REP>(x64, lane_sc, sv, cv);
 }
 
 // kappa = s2 exp(nh sin^2(pi d/p)) with sin^2 = (1 - cos(2 pi d/p)) / 2;  hsc2 = sc^2 / 2, invp64 = 64 / p

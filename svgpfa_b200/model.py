@@ -123,6 +123,7 @@ class B200SVLowerBound:
         self._leaf_list = None
         self._next_slot = 0
         self._spike_chunks = 0             # tuning / tests: neuron ranges per trial in the spike kernel (0 = automatic)
+        self._quad_warps = 0               # tuning: warps per CTA of the quadrature kernels (0 = automatic)
         self._kernels = None
         self._reg = None
         self._params_set = False
@@ -349,7 +350,7 @@ class B200SVLowerBound:
         dims = _cabi.Dims(R=R, N=N, K=K, Q=Q, KM=self._KM, MM=self._MM, PP=self._PP, TH=self._TH,
                           Mmax=max(self._M), n_ntiles=n_ntiles, S=self._S, reg=self._reg,
                           desc_host=ctypes.cast(self._desc_host, ctypes.POINTER(_cabi.LatentDesc)),
-                          spike_chunks=int(self._spike_chunks))
+                          spike_chunks=int(self._spike_chunks), quad_warps=int(self._quad_warps))
         self._dims = dims
         b = _cabi.Buffers()
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())

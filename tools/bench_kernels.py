@@ -1,11 +1,8 @@
-"""Times individual C-ABI stages (device time, CUDA events) on a config-#5-shaped shard.
-    python tools/bench_kernels.py [--trials 2000] [--stage spike_fwd_bwd] [--reps 5]
-Environment SVGPFA_SPIKE_VARIANT is read by the library once per process, so variants are run in
-separate processes (see --sweep)."""
+"""Times individual C-ABI stages (device time, CUDA events) on a shard of a BASELINE.json configuration.
+    python tools/bench_kernels.py [--config config5] [--trials 2000] [--reps 5] [--quad-warps N] [--flags F]"""
 import argparse
 import ctypes
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,22 +15,17 @@ def main():
     ap.add_argument("--config", default="config5")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--flags", type=int, default=15)
-    ap.add_argument("--sweep", default="")
+    ap.add_argument("--quad-warps", type=int, default=0)
+    ap.add_argument("--spike-chunks", type=int, default=0)
     args = ap.parse_args()
-    if args.sweep:
-        for v in args.sweep.split(","):
-            env = dict(os.environ, SVGPFA_SPIKE_VARIANT=v)
-            out = subprocess.run([sys.executable, __file__, "--trials", str(args.trials), "--config", args.config,
-                                  "--reps", str(args.reps), "--flags", str(args.flags)], env=env, capture_output=True, text=True)
-            print(f"variant {v}: {out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:]}")
-        return
     import torch
     from svgpfa_b200 import _cabi, synthetic
     from svgpfa_b200.testing import model_from_case, set_requires_grad
     dev = torch.device("cuda")
     cfg = dict(synthetic.CONFIGS[args.config], R=args.trials)
     case = synthetic.make_case_torch(cfg, dev, seed=0)
-    model = model_from_case(case, device=dev)
+    model = model_from_case(case, device=dev, spike_chunks=args.spike_chunks)
+    model._quad_warps = args.quad_warps
     set_requires_grad(model)
     lib = _cabi.lib()
     n_ev = len(_cabi.STAGES) + 1
@@ -56,7 +48,8 @@ def main():
         if rep > 0:
             for j in range(len(_cabi.STAGES)):
                 tot[j] += evs[j].elapsed_time(evs[j + 1]) / args.reps
-    print(" ".join(f"{n}={t:.3f}" for n, t in zip(_cabi.STAGES, tot)) + f" total={sum(tot):.3f} elbo={ref:.10e}")
+    print(f"{args.config} R={args.trials} qw={args.quad_warps} flags={args.flags}: " +
+          " ".join(f"{n}={t:.3f}" for n, t in zip(_cabi.STAGES, tot)) + f" total={sum(tot):.3f} elbo={ref:.10e}")
 
 
 if __name__ == "__main__":

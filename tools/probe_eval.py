@@ -12,11 +12,12 @@ from svgpfa_b200 import _cabi
 lib = _cabi.probes()
 dev = torch.device("cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-names = {20: "full", 21: "no moments", 22: "no table LDS", 23: "no spike-time LDS"}
+names = {20: "full", 21: "no moments", 22: "no table LDS", 23: "no spike-time LDS", 24: "degree-3 polynomial",
+         25: "I2F range reduction", 26: "degree 3 + I2F", 27: "degree 3 + I2F + pre-scaled t"}
 for per_sm in (5, 3, 2, 1):
     blocks = 148 * per_sm
     out = torch.zeros(blocks * 128, dtype=torch.float64, device=dev)
-    for kind in (20, 21, 22, 23):
+    for kind in (20, 21, 22, 23, 24, 25, 26, 27):
         iters = 40000
         best = 1e9
         for _ in range(3):
