@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 3
+#define SVGPFA_ABI_VERSION 4
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -53,8 +53,24 @@ enum {
     SVGPFA_GRAD_INDLOCS   = 8,     /* Z                    (ind.-points M-step, svEM.py:256-264) */
     SVGPFA_GRAD_ALL       = 15,
     SVGPFA_REUSE_KZZ      = 16,    /* L, Li, logdet already valid for the current (Z, theta)   */
-    SVGPFA_REUSE_SPIKE    = 32     /* abar_spk already valid for the current (Z, theta, C)     */
+    SVGPFA_REUSE_SPIKE    = 32,    /* abar_spk already valid for the current (Z, theta, C)     */
+    SVGPFA_REBUILD_PANELS = 64     /* spike_method = PANEL: rebuild pm_tau for the trial range first (new spikes) */
 };
+
+/* How the spike-time term is evaluated (svgpfa_dims.spike_method).
+ *   DIRECT  every (spike, latent, inducing point) kernel value is computed: S*K*M evaluations (svgpfa_spike_fwd_bwd).
+ *   PANEL   the term only ever needs sums  sum_s c_s f(t_s)  of functions f in the span of kappa_k(. - z_j) and their
+ *           parameter derivatives -- all analytic in t.  The time axis [pm_lo, pm_lo + pm_B*pm_w] is cut into pm_B
+ *           panels; on each, f is replaced by its interpolant at SVGPFA_PM_P first-kind Chebyshev nodes, so
+ *               sum_{s in (r,n)} f(t_s) = sum_i tau[r][n][i] f(t_i),   tau[r][n][i] = sum_{s in (r,n)} l_i(t_s)
+ *           with l_i the Lagrange cardinal functions of the panel nodes: the spikes enter only through the STATIC
+ *           "panel moments" tau (svgpfa_panel_moments, once per data set), and an evaluation costs
+ *           R*NB*(K*M kernel values + two skinny GEMMs over N) with NB = pm_B*SVGPFA_PM_P nodes per trial instead of
+ *           S_r spikes (config #5: 128 nodes against ~10^4 spikes per trial).  Interpolation error for the
+ *           exponential-quadratic kernel with panel half-width h <= 0.625 lengthscale: <= 3e-14 relative (tests);
+ *           the caller picks pm_B from the current hyper-parameters and falls back to DIRECT when it cannot. */
+enum { SVGPFA_SPIKE_DIRECT = 1, SVGPFA_SPIKE_PANEL = 2 };
+#define SVGPFA_PM_P 16             /* Chebyshev nodes per panel */
 
 enum {
     SVGPFA_OK = 0, SVGPFA_E_ARG = -1, SVGPFA_E_CUDA = -2, SVGPFA_E_UNSUPPORTED = -3,
@@ -86,7 +102,10 @@ typedef struct svgpfa_dims {
     int32_t spike_chunks;         /* tuning: neuron ranges per trial in the spike kernel's grid; 0 = automatic
                                      (tests force 1: whole-trial ranges, several spike tiles per CTA) */
     int32_t quad_warps;           /* tuning: warps per CTA of the M <= 32 quadrature kernels (one 32-point tile per warp
-                                     and pass); 0 = automatic (min(ceil(Q/32), 7)) */
+                                     and pass); 0 = automatic */
+    int32_t spike_method;         /* SVGPFA_SPIKE_*; 0 = DIRECT */
+    int32_t pm_B;                 /* PANEL: panels per trial: 4, 8, 12, 16, 24 or 32 */
+    double  pm_lo, pm_w;          /* PANEL: start of the first panel, panel width (same for every trial of the shard) */
 } svgpfa_dims;
 
 #define SVGPFA_NTRIALS(d) ((d)->rn ? (d)->rn : (d)->R)
@@ -129,6 +148,10 @@ typedef struct svgpfa_buffers {
     double* term1_part;          /* SVGPFA_TERM1_SLOTS partial sums of the intensity integral  */
     double* fin_part;            /* 3*SVGPFA_FIN_SLOTS per-block partials of svgpfa_finalize (KL, term1, term2), summed in
                                     fixed order: the bound is run-to-run reproducible given its inputs */
+    /* ---- panel path of the spike-time term (spike_method = SVGPFA_SPIKE_PANEL) ----------- */
+    double* pm_tau;              /* R*N*NB   [r][n][i]  static panel moments of every (trial, neuron) spike train      */
+    double* pm_mun;              /* R*K*NB   [r][k][i]  latent means at the panel nodes                                */
+    double* pm_mt;               /* R*K*NB   [r][k][i]  node weights  sum_n C[n,k] tau[r][n][i]                        */
     /* ---- cached-statistics path (embedding M-step) -------------------------------------- */
     double* mu_s;                /* S*K   latent means at spike times, [s][k]                   */
     /* ---- outputs ------------------------------------------------------------------------ */
@@ -184,6 +207,14 @@ int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, u
  * is not computed), LinearSVEmbeddingAssocTimes._compute... (svEmbedding.py:137-144) and
  * PointProcessELLExpLink._getELogLinkValues (expectedLogLikelihood.py:210-213). */
 int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
+
+/* The same term and the same outputs through the panel moments (see SVGPFA_SPIKE_PANEL above).
+ *   svgpfa_panel_moments       : pm_tau from spike_t / seg_off for the trial range (static: once per data set and
+ *                                panelisation)
+ *   svgpfa_spike_panel_fwd_bwd : pm_mun (latent means at the nodes), pm_mt = C^T tau, dC += tau mun^T, then abar_spk,
+ *                                dz_acc, dth_part from the node weights -- kernel values at R*K*M*NB points */
+int svgpfa_panel_moments(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+int svgpfa_spike_panel_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 
 /* (ii)+(v) adjoints through alpha, c, X, the KL term and the Cholesky factorisation: gm, gcholvec,
  * gZ, dth_part.  The reference obtains these from torch.autograd. */

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -22,7 +22,9 @@ SHARED_STATUS = 5            # shared[5..7] = (status, trial, latent) of a faile
 KERNEL_EXPQUAD, KERNEL_PERIODIC = 0, 1
 GRAD_POSTERIOR, GRAD_EMBEDDING, GRAD_KERNEL, GRAD_INDLOCS = 1, 2, 4, 8
 GRAD_ALL = 15
-REUSE_KZZ, REUSE_SPIKE = 16, 32
+REUSE_KZZ, REUSE_SPIKE, REBUILD_PANELS = 16, 32, 64
+SPIKE_DIRECT, SPIKE_PANEL = 1, 2
+PM_P = 16
 INFO_NOT_PD = 1
 
 
@@ -33,13 +35,14 @@ class LatentDesc(C.Structure):
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("R", "N", "K", "Q", "KM", "MM", "PP", "TH", "Mmax", "n_ntiles")] + [
         ("S", C.c_int64), ("reg", C.c_double), ("desc_host", C.POINTER(LatentDesc)), ("r0", C.c_int32), ("rn", C.c_int32),
-        ("spike_chunks", C.c_int32), ("quad_warps", C.c_int32)]
+        ("spike_chunks", C.c_int32), ("quad_warps", C.c_int32), ("spike_method", C.c_int32), ("pm_B", C.c_int32),
+        ("pm_lo", C.c_double), ("pm_w", C.c_double)]
 
 
 BUFFER_FIELDS = (
     "desc", "kscale", "theta", "Z", "m", "cholvec", "C", "d", "tq", "wq", "spike_t", "seg_off", "spike_cnt",
     "L", "Li", "X", "c", "alpha", "logdetL", "kl_rk", "A_q", "abar_q", "abar_spk", "dz_acc", "dth_part",
-    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "mu_s",
+    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "pm_tau", "pm_mun", "pm_mt", "mu_s",
     "shared", "gZ", "gm", "gcholvec", "info")
 
 
@@ -67,6 +70,8 @@ SYMBOLS = {
     "svgpfa_quad_embed_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_quad_latent_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_spike_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
+    "svgpfa_panel_moments": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
+    "svgpfa_spike_panel_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_indpoints_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_finalize": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_elbo_grad": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),

@@ -205,7 +205,11 @@ int run_trial_stages(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_
     if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_EMBED, st);
     if (flags & lat) { rc = svgpfa_quad_latent_bwd(dims, buf, flags, stream); if (rc) return rc; }
     if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_BWD, st);
-    if (!reuse_spike) { rc = svgpfa_spike_fwd_bwd(dims, buf, flags, stream); if (rc) return rc; }
+    if (!reuse_spike) {
+        rc = dims->spike_method == SVGPFA_SPIKE_PANEL ? svgpfa_spike_panel_fwd_bwd(dims, buf, flags, stream)
+                                                      : svgpfa_spike_fwd_bwd(dims, buf, flags, stream);
+        if (rc) return rc;
+    }
     if (mark) stage_mark(1 + SVGPFA_STAGE_SPIKE, st);
     if (flags & lat) { rc = svgpfa_indpoints_bwd(dims, buf, flags, stream); if (rc) return rc; }
     if (mark) stage_mark(1 + SVGPFA_STAGE_INDPOINTS_BWD, st);
@@ -338,7 +342,8 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
     if (!dims->desc_host) return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host: dims.desc_host", cudaSuccess);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = dims->R, D = sizeof(double);
-    const uint32_t flags_run = flags & ~(uint32_t)(SVGPFA_REUSE_KZZ | SVGPFA_REUSE_SPIKE);   // every input is new
+    uint32_t flags_run = flags & ~(uint32_t)(SVGPFA_REUSE_KZZ | SVGPFA_REUSE_SPIKE);   // every input is new
+    if (io->copy_static && dims->spike_method == SVGPFA_SPIKE_PANEL) flags_run |= SVGPFA_REBUILD_PANELS;   // new spikes
 #define CPY(dst, src, bytes, kind, s_)                                                                \
     do {                                                                                              \
         if ((bytes) > 0 && (dst) && (src)) {                                                          \

@@ -124,6 +124,8 @@ class B200SVLowerBound:
         self._next_slot = 0
         self._spike_chunks = 0             # tuning / tests: neuron ranges per trial in the spike kernel (0 = automatic)
         self._quad_warps = 0               # tuning: warps per CTA of the quadrature kernels (0 = automatic)
+        self.spike_method = "auto"         # "auto" | "direct" | "panel": how the spike-time term is evaluated
+        self._pm = None                    # state of the panel path: dict(B, lo, w, theta_version, built)
         self._kernels = None
         self._reg = None
         self._params_set = False
@@ -179,7 +181,8 @@ class B200SVLowerBound:
                                        self._thoff[k], self._P[k], self._nth[k])
         self._desc_host = desc
         self._desc_dev = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.int32).to(dev)
-        self._kscale = torch.tensor([[s[1], s[2], s[3], 0.0] for s in specs], dtype=_F64).to(dev).contiguous()
+        self._kscale_host = [[s[1], s[2], s[3], 0.0] for s in specs]
+        self._kscale = torch.tensor(self._kscale_host, dtype=_F64).to(dev).contiguous()
 
     def _make_views(self):
         """The leaf tensors the getters hand out: views of the packed K-major buffers (the optimiser's in-place
@@ -272,6 +275,12 @@ class B200SVLowerBound:
         else:
             st = torch.from_numpy(np.ascontiguousarray(np.asarray(spike_times)).astype(np.float64)).to(dev)
         self._S = int(st.numel())
+        if self._S:
+            lo_hi = torch.stack([st.min(), st.max()]).cpu()
+            self._t_lo, self._t_hi = float(lo_hi[0]), float(lo_hi[1])
+        else:
+            self._t_lo, self._t_hi = 0.0, 1.0
+        self._pm = None
         self._seg_off, self._spike_t, self._spike_cnt = seg.contiguous(), st.reshape(-1), cnt.contiguous()
         self._spike_R, self._spike_N = int(R), int(N)
         self._spikes_set = True
@@ -361,7 +370,9 @@ class B200SVLowerBound:
         for name, t in ws.items():
             setattr(b, name, ptr(t))
         b.mu_s = None
+        b.pm_tau = b.pm_mun = b.pm_mt = None
         self._bufs = b
+        self._pm = None
         self._ready = True
         self._kzz_key = self._spike_key = None
 
@@ -378,9 +389,77 @@ class B200SVLowerBound:
         self._kzz_key = None
         self._spike_key = None
 
+    # ------------------------------------------------------------------ spike-term method (include/svgpfa_b200.h)
+    PANEL_COUNTS = (4, 8, 12, 16, 24, 32)
+    PANEL_BETA = {_cabi.KERNEL_EXPQUAD: 0.625, _cabi.KERNEL_PERIODIC: 0.55}
+
+    def _panels_required(self, theta_host):
+        """Smallest panel count for which the 16-node interpolation of every latent's kernel (and of its parameter
+        derivatives) is accurate to ~3e-14 of the sums it replaces: panel half-width <= beta x (scale of variation).
+        Exponential-quadratic: the length scale, beta = 0.625.  Periodic, exp(-2 sin^2(pi d/p)/l^2): p min(l, 1)/(2 pi)
+        -- a Gaussian of that length scale near d = 0 for small l, harmonics of the period for large l -- beta = 0.55.
+        Calibrated in tools/panel_accuracy.py (numpy, long sums of random weights), checked on the GPU in
+        tests/test_gpu_panel.py."""
+        span = max(self._t_hi - self._t_lo, 1e-300)
+        need = 1
+        for k in range(self._K):
+            ktype = self._desc_host[k].ktype
+            th = theta_host[self._thoff[k]:self._thoff[k + 1]]
+            ell = abs(float(th[0])) * float(self._kscale_host[k][1])
+            if ktype == _cabi.KERNEL_PERIODIC:
+                ell = min(ell, 1.0) * abs(float(th[1])) * float(self._kscale_host[k][2]) / (2.0 * math.pi)
+            need = max(need, math.ceil(span / (2.0 * self.PANEL_BETA[ktype] * max(ell, 1e-300)) - 1e-9))
+        return need
+
+    def _select_spike_method(self):
+        """Chooses DIRECT or PANEL for the current hyper-parameters (they fix the panel count) and (re)builds the
+        static panel moments when the panelisation changed.  Costs one small device->host copy when theta changed."""
+        dims, b, dev = self._dims, self._bufs, self._dev()
+        ver = self._thbuf._version
+        if self._pm is not None and self._pm["theta_version"] == ver:
+            return
+        if self.spike_method == "direct" or self._S == 0 or self._N == 0:
+            dims.spike_method = _cabi.SPIKE_DIRECT
+            self._pm = dict(B=0, theta_version=ver)
+            return
+        need = self._panels_required(self._thbuf.detach().cpu().numpy())
+        B = next((c for c in self.PANEL_COUNTS if c >= need), None)
+        use = B is not None
+        if use and self.spike_method == "auto":
+            NB, KM, Kp = B * _cabi.PM_P, self._KM, 8 * ((self._K + 7) // 8)
+            panel_cost = self._R * NB * (30.0 * KM + 2.0 * self._N * Kp + 45.0 * self._N)
+            direct_cost = 13.0 * self._S * KM
+            tau_bytes = 8.0 * self._R * self._N * NB
+            use = (1.5 * panel_cost < direct_cost and self._K <= 40 and self._N <= 8000
+                   and tau_bytes <= 0.3 * torch.cuda.get_device_properties(dev).total_memory)
+        if not use:
+            if self.spike_method == "panel":
+                raise RuntimeError(f"spike_method='panel' needs {need} panels (> 32) for the current kernel parameters")
+            dims.spike_method = _cabi.SPIKE_DIRECT
+            self._pm = dict(B=0, theta_version=ver)
+            return
+        old = self._pm or {}
+        if old.get("B") != B:
+            NB = B * _cabi.PM_P
+            lo = self._t_lo
+            w = (self._t_hi - self._t_lo) / B * (1.0 + 1e-12) if self._t_hi > self._t_lo else 1.0 / B
+            self._ws["pm_tau"] = torch.empty(self._R * self._N * NB, dtype=_F64, device=dev)
+            self._ws["pm_mun"] = torch.empty(self._R * self._K * NB, dtype=_F64, device=dev)
+            self._ws["pm_mt"] = torch.empty(self._R * self._K * NB, dtype=_F64, device=dev)
+            for name in ("pm_tau", "pm_mun", "pm_mt"):
+                setattr(b, name, self._ws[name].data_ptr())
+            dims.spike_method, dims.pm_B, dims.pm_lo, dims.pm_w = _cabi.SPIKE_PANEL, B, lo, w
+            with torch.cuda.device(dev):
+                _cabi.check(_cabi.lib().svgpfa_panel_moments(ctypes.byref(dims), ctypes.byref(b), self._stream()),
+                            "panel_moments")
+            self._spike_key = None
+        dims.spike_method = _cabi.SPIKE_PANEL
+        self._pm = dict(B=B, theta_version=ver)
+
     def _run(self, flags):
         """One fused value+gradient pass (svgpfa_elbo_grad).  Returns (shared, gZ, gm, gcholvec)."""
         self._prepare()
+        self._select_spike_method()
         dev = self._dev()
         R = self._R
         kz_key = self._param_versions()
@@ -503,6 +582,7 @@ class B200SVLowerBound:
         ``svgpfa_elbo_grad``, device->host copies of the bound and the gradients, all on the current
         stream; returns after the stream has drained.  Returns (elbo, h2d_bytes, d2h_bytes)."""
         self._prepare()
+        self._select_spike_method()      # from the DEVICE copy of theta (the host copy is expected to hold the same values)
         dev = self._dev()
         R = self._R
         b = _cabi.Buffers.from_buffer_copy(self._bufs)
@@ -635,7 +715,7 @@ class B200SVLowerBound:
     # the kernel objects' parameter tensors, which alias the same packed buffer -- are NOT part of the state: they
     # are rebuilt from the packed buffers on load, with their requires_grad flags.
     _TRANSIENT = ("_bufs", "_dims", "_desc_host", "_desc_dev", "_ws", "_cached_keepalive", "_pg", "_Z", "_m", "_cv",
-                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared")
+                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared", "_pm")
 
     def __getstate__(self):
         self._poll_errors(block=True)
@@ -663,6 +743,7 @@ class B200SVLowerBound:
         self._kernels = None
         self._leaf_list = None
         self._last_shared = None
+        self._pm = None
         if kernels is not None:
             self._kernels = []
             for cls, kst in kernels:

@@ -22,7 +22,7 @@ def initial_params_from_case(case, device=None):
 
 
 def model_from_case(case, device=None, process_group=None, nested=False, check_errors=True, shard_mode="auto",
-                    spike_chunks=0):
+                    spike_chunks=0, spike_method="auto"):
     """A fully specified ``B200SVLowerBound`` for ``case``.  ``nested=True`` feeds the spikes
     through ``setMeasurements`` (nested python lists, the reference's format) instead of the
     flat fast path."""
@@ -30,6 +30,7 @@ def model_from_case(case, device=None, process_group=None, nested=False, check_e
     model = B200SVLowerBound(kernels=build_kernels(case["kernel_types"]), device=device,
                              process_group=process_group, check_errors=check_errors, shard_mode=shard_mode)
     model._spike_chunks = spike_chunks
+    model.spike_method = spike_method
     model.setInitialParams(initial_params_from_case(case))
     if nested:
         model.setMeasurements(nested_spikes(case))

@@ -56,7 +56,7 @@ def test_abi_constants_match_header(lib):
     fields = re.findall(r"\*\s*([A-Za-z_0-9]+);", body)
     assert tuple(fields) == _cabi.BUFFER_FIELDS
     assert ctypes.sizeof(_cabi.LatentDesc) == 32
-    assert ctypes.sizeof(_cabi.Dims) == 80
+    assert ctypes.sizeof(_cabi.Dims) == 104
     assert get("SVGPFA_FIN_SLOTS") == _cabi.FIN_SLOTS
 
 
