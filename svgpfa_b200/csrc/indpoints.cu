@@ -490,6 +490,274 @@ __global__ void __launch_bounds__(IP_BWD_THREADS) indpoints_bwd_kernel(svgpfa_di
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// M <= 32: the same adjoint with compile-time shapes.  What ncu showed of the kernel above (round 1: 27 900 warp
+// instructions per matrix for ~650 DMMAs, issue slots 44 % busy, FP64 pipe 5 %): the generic lambdas cost ~40
+// instructions per mma.  Here warp `it` owns the 8-row tile `it` of every product and all its column tiles (one A
+// fragment per k-step shared by the MT column tiles), the k range of each (row, column) tile is a compile-time-unrolled
+// predicated loop, and a CTA is MT warps, so ~2.3 instructions per mma and 4-5 CTAs per SM.
+// Same algebra, same buffers and the same order of the nine products as indpoints_bwd_kernel.
+// ------------------------------------------------------------------------------------------
+// acc(jt) = sum_{ks in [lo(jt), hi(jt)]} A(8 it + g, 4 ks + tg) B(4 ks + tg, 8 jt + g);  TA / TB: operand stored transposed
+template <int MT, bool TA, bool TB, class FR, class FO>
+__device__ __forceinline__ void ipb_product(const double* __restrict__ A, const double* __restrict__ B, int it, int lane,
+                                            FR range, FO out) {
+    constexpr int LD = 8 * MT + 4, KS = 2 * MT;
+    const int g = lane >> 2, tg = lane & 3;
+    double acc[MT][2];
+    int lo[MT], hi[MT];
+#pragma unroll
+    for (int jt = 0; jt < MT; ++jt) {
+        acc[jt][0] = acc[jt][1] = 0.0;
+        range(it, jt, lo[jt], hi[jt]);                    // k-steps; hi < lo: the tile is not needed
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const double a = TA ? A[(4 * ks + tg) * LD + 8 * it + g] : A[(8 * it + g) * LD + 4 * ks + tg];
+#pragma unroll
+        for (int jt = 0; jt < MT; ++jt) {
+            if (ks >= lo[jt] && ks <= hi[jt]) {
+                const double b = TB ? B[(8 * jt + g) * LD + 4 * ks + tg] : B[(4 * ks + tg) * LD + 8 * jt + g];
+                dmma8(acc[jt][0], acc[jt][1], a, b);
+            }
+        }
+    }
+#pragma unroll
+    for (int jt = 0; jt < MT; ++jt) {
+        if (hi[jt] >= lo[jt]) {
+            out(8 * it + g, 8 * jt + 2 * tg, acc[jt][0]);
+            out(8 * it + g, 8 * jt + 2 * tg + 1, acc[jt][1]);
+        }
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(32 * MT) indpoints_bwd_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+    constexpr int MP = 8 * MT, LD = MP + 4, MS = MP * LD, KS = 2 * MT, T = 32 * MT;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    const int M = ds.M;
+    const bool need_post = flags & SVGPFA_GRAD_POSTERIOR;
+    const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
+    double* Lm = sm;             // L
+    double* Li = Lm + MS;        // L^-1
+    double* X = Li + MS;         // L^-1 Ls
+    double* B3 = X + MS;
+    double* B4 = B3 + MS;
+    double* B5 = B4 + MS;
+    double* al = B5 + MS;        // alpha
+    double* cv = al + MP;        // c
+    double* yv = cv + MP;        // Li abar
+    double* mb = yv + MP;        // mbar
+    double* ab = mb + MP;        // abar total
+    double* zs = ab + MP;        // z
+    const int tid = threadIdx.x, lane = tid & 31, it = tid >> 5;
+    const size_t mo = (size_t)r * dm.MM + ds.mmoff, vo = (size_t)r * dm.KM + ds.moff;
+    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
+    if (M == MP && (mo & 1) == 0) {                      // whole 16-byte chunks: asynchronous copies
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(Lm);
+        for (int c = tid; c < MP * (MP / 2); c += T) {
+            const int i = c / (MP / 2), jj = c - i * (MP / 2);
+            const size_t go = mo + (size_t)i * M + 2 * jj;
+            const unsigned so = (unsigned)(i * LD + 2 * jj) * 8u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + so), "l"(bf.L + go) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + MS * 8u + so), "l"(bf.Li + go) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2u * MS * 8u + so), "l"(bf.X + go) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 3u * MS * 8u + so), "l"(bf.A_q + go) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        for (int idx = tid; idx < MP * MP; idx += T) {
+            const int i = idx / MP, j = idx - i * MP;
+            const bool in = i < M && j < M;
+            const size_t gi = mo + (size_t)i * M + j;
+            Lm[i * LD + j] = in ? bf.L[gi] : 0.0;
+            Li[i * LD + j] = in ? bf.Li[gi] : 0.0;
+            X[i * LD + j] = in ? bf.X[gi] : 0.0;
+            B3[i * LD + j] = in ? bf.A_q[gi] : 0.0;
+        }
+    }
+    const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
+    for (int i = tid; i < MP; i += T) {
+        const bool in = i < M;
+        al[i] = in ? bf.alpha[vo + i] : 0.0;
+        cv[i] = in ? bf.c[vo + i] : 0.0;
+        ab[i] = in ? bf.abar_q[vo + i] + bf.abar_spk[vo + i] : 0.0;
+        zs[i] = in ? zg[i] : 0.0;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // A_q is stored lower: mirror it
+    for (int idx = tid; idx < MP * MP; idx += T) {
+        const int i = idx / MP, j = idx - i * MP;
+        if (j > i) B3[i * LD + j] = B3[j * LD + i];
+    }
+    // y = Li abar: four threads per row (T / 4 = MP rows), two partial sums each -- a single thread per row was a
+    // chain of up to 32 dependent (LDS, LDS, DFMA) steps executed by one warp while the other three waited
+    {
+        const int i = tid >> 2, part = tid & 3;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int p = part; p < MP; p += 8) {              // Li is stored with zeros above the diagonal
+            s0 = fma(Li[i * LD + p], ab[p], s0);
+            s1 = fma(Li[i * LD + p + 4], ab[p + 4], s1);
+        }
+        double sy = s0 + s1;
+        sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+        sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+        if (part == 0) yv[i] = sy;
+    }
+    __syncthreads();
+    // Xbar = tril(2 A X) - X -> B4 (lower tiles; the strict upper part of the diagonal tiles is zeroed)
+    ipb_product<MT, false, false>(B3, X, it, lane,
+        [&](int i_t, int jt, int& lo, int& hi) { lo = 2 * jt; hi = jt <= i_t ? KS - 1 : -1; },
+        [&](int i, int j, double v) { B4[i * LD + j] = (j <= i) ? 2.0 * v - X[i * LD + j] : 0.0; });
+    // mbar = Li^T (y - c), four threads per column
+    {
+        const int j = tid >> 2, part = tid & 3;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = part; i < MP; i += 8) {
+            s0 = fma(Li[i * LD + j], yv[i] - cv[i], s0);
+            s1 = fma(Li[(i + 4) * LD + j], yv[i + 4] - cv[i + 4], s1);
+        }
+        double sm_ = s0 + s1;
+        sm_ += __shfl_xor_sync(0xffffffffu, sm_, 1);
+        sm_ += __shfl_xor_sync(0xffffffffu, sm_, 2);
+        if (part == 0) mb[j] = sm_;
+    }
+    __syncthreads();
+    // T = Li^T tril(Xbar) -> B5 (full)      T(i,j) = sum_{p >= max(i,j)} Li(p,i) Xbar(p,j)
+    ipb_product<MT, true, false>(Li, B4, it, lane,
+        [&](int i_t, int jt, int& lo, int& hi) { lo = 2 * max(i_t, jt); hi = KS - 1; },
+        [&](int i, int j, double v) { B5[i * LD + j] = v; });
+    __syncthreads();
+    if (need_post) {
+        double* gm = bf.gm + (size_t)dm.R * ds.moff + (size_t)r * M;
+        for (int i = tid; i < M; i += T) gm[i] = mb[i];
+        double* gcv = bf.gcholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
+        const double* cvec = bf.cholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
+        for (int p = tid; p < ds.P; p += T) {             // coalesced over the packed row-major tril vector
+            int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > p) --i;
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            const int j = p - i * (i + 1) / 2;
+            gcv[p] = B5[i * LD + j] + (i == j ? 1.0 / cvec[p] : 0.0);
+        }
+    }
+    if (!need_kz) return;
+    // B4 = X^T A      (i,j) = sum_{p >= i} X(p,i) A(p,j)
+    ipb_product<MT, true, false>(X, B3, it, lane,
+        [&](int i_t, int, int& lo, int& hi) { lo = 2 * i_t; hi = KS - 1; },
+        [&](int i, int j, double v) { B4[i * LD + j] = v; });
+    __syncthreads();
+    // B3 = E2 = X (X^T A) - A   (each element of B3 is read and written by its own thread only)
+    ipb_product<MT, false, false>(X, B4, it, lane,
+        [&](int i_t, int, int& lo, int& hi) { lo = 0; hi = 2 * i_t + 1; },
+        [&](int i, int j, double v) { B3[i * LD + j] = v - B3[i * LD + j]; });
+    __syncthreads();
+    // Lbar (lower) -> B4 = -2 Li^T E2 - alpha y^T - mbar c^T - diag(1/L_ii) [- T X^T below]
+    ipb_product<MT, true, false>(Li, B3, it, lane,
+        [&](int i_t, int jt, int& lo, int& hi) { lo = 2 * i_t; hi = jt <= i_t ? KS - 1 : -1; },
+        [&](int i, int j, double v) {
+            double s = 0.0;
+            if (j <= i && i < M) {
+                s = -2.0 * v - al[i] * yv[j] - mb[i] * cv[j];
+                if (i == j) s -= 1.0 / Lm[i * LD + i];
+            }
+            B4[i * LD + j] = s;
+        });
+    for (int idx = tid; idx < MP * MP; idx += T) {            // the skipped upper tiles of Lbar are zero
+        const int i = idx / MP, j = idx - i * MP;
+        if ((j >> 3) > (i >> 3)) B4[i * LD + j] = 0.0;
+    }
+    __syncthreads();
+    //   (T X^T)(i,j) = sum_{p <= j} T(i,p) X(j,p)
+    ipb_product<MT, false, true>(B5, X, it, lane,
+        [&](int i_t, int jt, int& lo, int& hi) { lo = 0; hi = jt <= i_t ? 2 * jt + 1 : -1; },
+        [&](int i, int j, double v) { if (j <= i) B4[i * LD + j] -= v; });
+    __syncthreads();
+    // P = Phi(L^T Lbar) -> B3 lower       (i,j) = sum_{p >= i} L(p,i) Lbar(p,j)      (diagonal: P_ii = s/2, S_ii = s)
+    ipb_product<MT, true, false>(Lm, B4, it, lane,
+        [&](int i_t, int jt, int& lo, int& hi) { lo = 2 * i_t; hi = jt <= i_t ? KS - 1 : -1; },
+        [&](int i, int j, double v) { if (j <= i) B3[i * LD + j] = v; });
+    __syncthreads();
+    for (int idx = tid; idx < MP * MP; idx += T) {          // S = P + P^T
+        const int i = idx / MP, j = idx - i * MP;
+        if (j > i) B3[i * LD + j] = B3[j * LD + i];
+    }
+    __syncthreads();
+    // U1 = S Li -> B4      (i,j) = sum_{p >= j} S(i,p) Li(p,j)
+    ipb_product<MT, false, false>(B3, Li, it, lane,
+        [&](int, int jt, int& lo, int& hi) { lo = 2 * jt; hi = KS - 1; },
+        [&](int i, int j, double v) { B4[i * LD + j] = v; });
+    __syncthreads();
+    // Kbar = 0.5 Li^T U1 -> B5      (i,j) = sum_{p >= i} Li(p,i) U1(p,j)
+    ipb_product<MT, true, false>(Li, B4, it, lane,
+        [&](int i_t, int, int& lo, int& hi) { lo = 2 * i_t; hi = KS - 1; },
+        [&](int i, int j, double v) { B5[i * LD + j] = 0.5 * v; });
+    // the exp / sincos tables of the last phase live in B3, which is free now (1.5 KB of static shared memory would
+    // cost the fourth resident CTA: 4 x 58 112 B is exactly the 227 KB of an SM)
+    double* etab = B3;
+    double2* sctab = reinterpret_cast<double2*>(B3 + 64);
+    svgpfa_load_exp_tab64(etab);
+    if (kc.type == SVGPFA_KERNEL_PERIODIC) svgpfa_load_sincos_tab<1>(sctab);
+    __syncthreads();
+    // dZ_i = 2 sum_j Kbar_ij dkappa/ddelta(z_i - z_j);  dtheta = sum_ij Kbar_ij dkappa/dtheta:
+    // thread <-> (row i, quarter of the columns), two kernel evaluations per iteration (kappa_vals_n)
+    double t0 = 0.0, t1 = 0.0;
+    double* gZ = bf.gZ + (size_t)dm.R * ds.moff + (size_t)r * M;
+    {
+        const int i = tid >> 2, part = tid & 3;          // T / 4 = MP rows
+        double dz = 0.0;
+        const double zi = zs[i];
+        constexpr int NE = (2 * MT) % 4 == 0 ? 4 : 2;     // MP / 4 = 2 MT columns per thread
+#pragma unroll 1
+        for (int j0 = part * (MP / 4); j0 < (part + 1) * (MP / 4); j0 += NE) {
+            double dl[NE], kv[NE], qq[NE], s2x[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) dl[e] = zi - zs[j0 + e];
+            kappa_vals_n<NE>(kc, dl, etab, sctab, kv, qq, s2x);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double h = (i < M && j0 + e < M) ? B5[i * LD + j0 + e] * kv[e] : 0.0;
+                if (kc.type == SVGPFA_KERNEL_EXPQUAD) {
+                    dz = fma(h, dl[e], dz);
+                    t0 = fma(h, qq[e], t0);
+                } else {
+                    const double hs = h * s2x[e];
+                    dz += hs;
+                    t0 = fma(h, qq[e], t0);
+                    t1 = fma(hs, dl[e], t1);
+                }
+            }
+        }
+        dz += __shfl_xor_sync(0xffffffffu, dz, 1);
+        dz += __shfl_xor_sync(0xffffffffu, dz, 2);
+        // dkappa/ddelta = kappa (delta | sin 2x) dd
+        if (i < M && part == 0 && (flags & SVGPFA_GRAD_INDLOCS)) gZ[i] = 2.0 * kc.dd * dz + bf.dz_acc[vo + i];
+    }
+    if (flags & SVGPFA_GRAD_KERNEL) {
+        const double s0 = block_sum(kc.dl * t0, red);
+        const double s1 = block_sum(kc.dp * t1, red);
+        if (tid == 0) {
+            double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
+            dth[0] += s0;
+            if (ds.nth > 1) dth[1] += s1;
+        }
+    }
+}
+
+template <int MT>
+void launch_ipb_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    constexpr int MP = 8 * MT, LD = MP + 4;
+    const size_t smem = sizeof(double) * ((size_t)6 * MP * LD + 6 * MP);
+    SVGPFA_ENSURE_SMEM(smem, indpoints_bwd_mma_kernel<MT>);
+    indpoints_bwd_mma_kernel<MT><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * MT, smem, st>>>(*dims, *buf, flags);
+}
+
 size_t ip_smem(int Mmax, int nmat, int nvec) {
     const int MP = (Mmax + 7) / 8 * 8, ld = MP + 4;      // covers both the odd-ld (M|1) and the padded (MP+4) layouts
     return sizeof(double) * ((size_t)nmat * MP * ld + (size_t)nvec * MP);
@@ -532,9 +800,18 @@ extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffer
 extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "indpoints_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    const size_t smem = ip_smem(dims->Mmax, 6, 6);
-    SVGPFA_ENSURE_SMEM(smem, indpoints_bwd_kernel);
-    indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_BWD_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    if (dims->Mmax <= 32) {
+        switch ((dims->Mmax + 7) / 8) {
+            case 1: launch_ipb_mma<1>(dims, buf, flags, (cudaStream_t)stream); break;
+            case 2: launch_ipb_mma<2>(dims, buf, flags, (cudaStream_t)stream); break;
+            case 3: launch_ipb_mma<3>(dims, buf, flags, (cudaStream_t)stream); break;
+            default: launch_ipb_mma<4>(dims, buf, flags, (cudaStream_t)stream); break;
+        }
+    } else {
+        const size_t smem = ip_smem(dims->Mmax, 6, 6);
+        SVGPFA_ENSURE_SMEM(smem, indpoints_bwd_kernel);
+        indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_BWD_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    }
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;
 }

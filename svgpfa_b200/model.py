@@ -411,18 +411,20 @@ class B200SVLowerBound:
             need = max(need, math.ceil(span / (2.0 * self.PANEL_BETA[ktype] * max(ell, 1e-300)) - 1e-9))
         return need
 
-    def _select_spike_method(self):
+    def _select_spike_method(self, theta_host=None, build=True):
         """Chooses DIRECT or PANEL for the current hyper-parameters (they fix the panel count) and (re)builds the
-        static panel moments when the panelisation changed.  Costs one small device->host copy when theta changed."""
+        static panel moments when the panelisation changed.  Costs one small device->host copy when theta changed.
+        ``theta_host``: take the hyper-parameters from this host array instead (host-buffer entry: the device copy
+        is about to be overwritten); ``build=False``: the caller rebuilds the moments itself (new spikes)."""
         dims, b, dev = self._dims, self._bufs, self._dev()
-        ver = self._thbuf._version
+        ver = self._thbuf._version if theta_host is None else ("host", tuple(np.asarray(theta_host).tolist()))
         if self._pm is not None and self._pm["theta_version"] == ver:
             return
         if self.spike_method == "direct" or self._S == 0 or self._N == 0:
             dims.spike_method = _cabi.SPIKE_DIRECT
             self._pm = dict(B=0, theta_version=ver)
             return
-        need = self._panels_required(self._thbuf.detach().cpu().numpy())
+        need = self._panels_required(self._thbuf.detach().cpu().numpy() if theta_host is None else np.asarray(theta_host))
         B = next((c for c in self.PANEL_COUNTS if c >= need), None)
         use = B is not None
         if use and self.spike_method == "auto":
@@ -449,9 +451,10 @@ class B200SVLowerBound:
             for name in ("pm_tau", "pm_mun", "pm_mt"):
                 setattr(b, name, self._ws[name].data_ptr())
             dims.spike_method, dims.pm_B, dims.pm_lo, dims.pm_w = _cabi.SPIKE_PANEL, B, lo, w
-            with torch.cuda.device(dev):
-                _cabi.check(_cabi.lib().svgpfa_panel_moments(ctypes.byref(dims), ctypes.byref(b), self._stream()),
-                            "panel_moments")
+            if build:
+                with torch.cuda.device(dev):
+                    _cabi.check(_cabi.lib().svgpfa_panel_moments(ctypes.byref(dims), ctypes.byref(b), self._stream()),
+                                "panel_moments")
             self._spike_key = None
         dims.spike_method = _cabi.SPIKE_PANEL
         self._pm = dict(B=B, theta_version=ver)
@@ -582,7 +585,7 @@ class B200SVLowerBound:
         ``svgpfa_elbo_grad``, device->host copies of the bound and the gradients, all on the current
         stream; returns after the stream has drained.  Returns (elbo, h2d_bytes, d2h_bytes)."""
         self._prepare()
-        self._select_spike_method()      # from the DEVICE copy of theta (the host copy is expected to hold the same values)
+        self._select_spike_method(theta_host=io["theta"].numpy(), build=not copy_static)
         dev = self._dev()
         R = self._R
         b = _cabi.Buffers.from_buffer_copy(self._bufs)
@@ -606,6 +609,8 @@ class B200SVLowerBound:
                 io["shared"].copy_(shared, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         self._kzz_key = self._spike_key = None
+        if self._pm is not None:
+            self._pm["theta_version"] = None        # the device parameters were replaced: re-derive at the next eval()
         nb = lambda *names: sum(io[n].numel() * io[n].element_size() for n in names)
         h2d = nb("theta", "Z", "m", "cholvec", "C", "d")
         if copy_static:

@@ -157,7 +157,6 @@ def test_host_buffer_entry_rebuilds_panels():
     want = ref.eval().item()
     model = model_from_case(case, spike_method="panel")
     io = model.makeHostIO(pin=True)
-    model._ws_probe = None
     model.eval()
     model._ws["pm_tau"].fill_(float("nan"))            # a missed rebuild cannot go unnoticed
     for nb in (1, 3):
