@@ -219,6 +219,13 @@ def measure_peaks(device):
     return res
 
 
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6553.9                                         # the pool's measured copy bandwidth (B200_PROFILING.md)
+
+
 def algorithmic_counts(cfg, R, S):
     """SURVEY.md §8d per-unit work formulas for R trials holding S spikes."""
     N, K, M, Q = cfg["N"], cfg["K"], cfg["M"], cfg["Q"]
@@ -429,60 +436,65 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (FP64 pipe; see DESIGN.md "Roofline model")
+    # ---- roofline (FP64 pipe; see DESIGN.md "Roofline model"): every stage against the DFMA peak measured in this run
+    # with SURVEY.md 8d's algorithmic flop counts (+ 26 flop-equivalents = 13 FP64 instruction slots per kernel
+    # evaluation / exp); `roofline` itself describes the stage that takes the most time
     peaks = measure_peaks(device)
-    cnt = algorithmic_counts(cfg, r1 - r0, S_local)
-    spike_idx = _cabi.STAGES.index("spike_fwd_bwd")
-    t_spike = float(st[spike_idx]) * 1e-3
+    Rl = r1 - r0
+    cnt = algorithmic_counts(cfg, Rl, S_local)
     peak_tf = 2.0 * peaks["dfma"] / 1e12
-    # primary: minimal FP64-pipe instruction slots of the algorithm per (spike, latent, inducing point):
-    # delta, delta^2, *(-1/2l^2), exp (7), sum kappa, sum kappa delta, sum kappa delta^2 = 13 (+ sincospi
-    # for periodic kernels, at its measured cost); one slot = one FMA = 2 flops.
-    c_sin = peaks["dfma"] / peaks["sincospi"]
-    slots = 13.0 * cnt["N_exp_spike"] + (c_sin + 3.0) * cnt["N_sin_spike"]
-    achieved = 2.0 * slots / t_spike / 1e12
-    # secondary: SURVEY.md 8d cost model (10 M flops per spike-latent + one exp at the libdevice exp's measured cost)
-    c_exp_libdevice = 2.0 * peaks["dfma"] / peaks["exp"]
-    survey_flops = cnt["F_spike"] + cnt["N_exp_spike"] * c_exp_libdevice + cnt["N_sin_spike"] * 2.0 * c_sin
-    roofline = {"bound": "fp64", "kernel": "spike_tile_kernel", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                "peak_source": "DFMA throughput measured in this run (svgpfa_peak_probe); MEASURED_PEAKS.json has "
-                               "no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
-                "model": "algorithmic FP64 instruction slots x 2 flops: 13 per (spike, latent, inducing point)",
-                "algorithmic": {"kernel_evals": cnt["N_exp_spike"], "periodic_evals": cnt["N_sin_spike"],
-                                "fp64_slots": slots},
-                "frac_survey_model": survey_flops / t_spike / 1e12 / peak_tf,
-                "survey_model": {"flops": cnt["F_spike"], "exp": cnt["N_exp_spike"],
-                                 "flops_per_libdevice_exp": c_exp_libdevice},
-                "share_of_step": t_spike * 1e3 / float(st.sum()),
-                "launch_ms": t_spike * 1e3}
-    total_equiv = (cnt["F_setup"] + cnt["F_quad"] + cnt["F_embed"] + 2.0 * slots
-                   + cnt["N_exp_other"] * 2.0 * 7.0)
-    roofline["whole_step_frac"] = total_equiv / (ms_step * 1e-3) / 1e12 / peak_tf
-    # every other stage against the same FP64 peak with SURVEY.md 8d's flop counts (an exp counted at 2 x 13 flops, the
-    # library's instruction count): how far each fused kernel is from the FP64 roof, not only the dominant one
     stage = {n: float(v) * 1e-3 for n, v in zip(_cabi.STAGES, st)}
-    Rl, K_, M_, Q_, N_ = r1 - r0, cfg["K"], cfg["M"], cfg["Q"], cfg["N"]
+    K_, M_, Q_, N_ = cfg["K"], cfg["M"], cfg["Q"], cfg["N"]
     exp_fl = 26.0
-
-    def frac_of(flops, seconds):
-        return None if seconds <= 0 else flops / seconds / 1e12 / peak_tf
-    roofline["other_stages"] = {
-        "model": "SURVEY.md 8d flop counts (split between forward and backward as 1:2) + 26 flop-equivalents per "
-                 "kernel evaluation / exp, over the stage's CUDA-event time, as a fraction of the same measured DFMA peak",
-        "kzz_chol+indpoints_fwd+indpoints_bwd": frac_of(cnt["F_setup"] + exp_fl * Rl * K_ * M_ * (M_ + 1),
-                                                        stage["kzz_chol"] + stage["indpoints_fwd"] + stage["indpoints_bwd"]),
-        "quad_latent_fwd": frac_of(cnt["F_quad"] / 3.0 + exp_fl * Rl * K_ * Q_ * M_, stage["quad_latent_fwd"]),
-        "quad_latent_bwd": frac_of(cnt["F_quad"] * 2.0 / 3.0 + exp_fl * 2.0 * Rl * K_ * Q_ * M_, stage["quad_latent_bwd"]),
-        "quad_embed": frac_of(cnt["F_embed"] + exp_fl * Rl * Q_ * N_, stage["quad_embed"]),
+    panel = model._dims.spike_method == _cabi.SPIKE_PANEL
+    NB = model._dims.pm_B * _cabi.PM_P if panel else 0
+    c_sin = peaks["dfma"] / peaks["sincospi"]
+    direct_flops = 2.0 * (13.0 * cnt["N_exp_spike"] + (c_sin + 3.0) * cnt["N_sin_spike"])
+    flops = {
+        "kzz_chol+indpoints_fwd+indpoints_bwd": cnt["F_setup"] + exp_fl * Rl * K_ * M_ * (M_ + 1),
+        "quad_latent_fwd": cnt["F_quad"] / 3.0 + exp_fl * Rl * K_ * Q_ * M_,
+        "quad_embed": cnt["F_embed"] + exp_fl * Rl * Q_ * N_,
+        "quad_latent_bwd": cnt["F_quad"] * 2.0 / 3.0 + exp_fl * 2.0 * Rl * K_ * Q_ * M_,
+        # panel path: kernel values at the NB nodes of every (trial, latent, inducing point), twice (latent means at the
+        # nodes, then the adjoints), and the two skinny GEMMs over the panel moments (2 flops per multiply-add)
+        "spike_fwd_bwd": (exp_fl * 2.0 * Rl * K_ * M_ * NB + 4.0 * Rl * N_ * NB * K_) if panel else direct_flops,
     }
-    try:        # DRAM traffic of the launch from the committed ncu --set full capture of the same configuration
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_spike_traffic.json"))).get(args.config)
-        if tr and tr["trials"] == r1 - r0:
-            roofline["traffic"] = tr["dram_bytes_per_launch"]
-            roofline["traffic_note"] = ("ncu dram bytes per launch; algorithmic minimum 8 B x spikes = %.2e: every spike "
-                                        "is re-read by the ceil(K*M/128) CTAs that cover the (latent, inducing point) "
-                                        "pairs of its trial; 57 GB/s, far from the HBM roof" % (8.0 * S_local))
+    times = {"kzz_chol+indpoints_fwd+indpoints_bwd": stage["kzz_chol"] + stage["indpoints_fwd"] + stage["indpoints_bwd"],
+             "quad_latent_fwd": stage["quad_latent_fwd"], "quad_embed": stage["quad_embed"],
+             "quad_latent_bwd": stage["quad_latent_bwd"], "spike_fwd_bwd": stage["spike_fwd_bwd"]}
+    total_t = float(st.sum()) * 1e-3
+    stages = {n: {"ms": times[n] * 1e3, "algorithmic_flops": flops[n],
+                  "frac": (flops[n] / times[n] / 1e12 / peak_tf) if times[n] > 0 else None,
+                  "share_of_step": times[n] / total_t} for n in flops}
+    dom = max(times, key=lambda n: times[n])
+    kernel_names = {"quad_latent_bwd": "quad_latent_mma_kernel<MT,true>", "quad_latent_fwd": "quad_latent_mma_kernel<MT,false>",
+                    "quad_embed": "quad_embed_mma_kernel", "spike_fwd_bwd": "panel_* kernels" if panel else "spike_tile_kernel",
+                    "kzz_chol+indpoints_fwd+indpoints_bwd": "kzz_chol_warp / indpoints_fwd_warp / indpoints_bwd_mma"}
+    roofline = {"bound": "fp64", "kernel": f"{dom}: {kernel_names[dom]}", "achieved": flops[dom] / times[dom] / 1e12,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": stages[dom]["frac"], "traffic": None,
+                "peak_source": "DFMA throughput measured in this run (probes library); MEASURED_PEAKS.json has no FP64 "
+                               "entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s; mma.m8n8k4.f64 runs on the "
+                               "same pipe at the same rate (tools/probe_dmma.py)",
+                "model": "SURVEY.md 8d flop counts (quadrature: 1/3 forward, 2/3 adjoint) + 26 flop-equivalents per kernel "
+                         "evaluation / exp, over the stage's CUDA-event time inside the timed region",
+                "share_of_step": times[dom] / total_t, "launch_ms": times[dom] * 1e3, "stages": stages,
+                "whole_step_frac": sum(flops.values()) / (ms_step * 1e-3) / 1e12 / peak_tf}
+    # the spike-time term: which algorithm ran, and what the direct evaluation of SURVEY.md 8d would have cost
+    roofline["spike_term"] = {
+        "method": "panel" if panel else "direct", "panels": int(model._dims.pm_B) if panel else 0, "nodes_per_trial": NB,
+        "direct_algorithmic_flops": direct_flops,
+        "direct_equivalent_frac": direct_flops / times["spike_fwd_bwd"] / 1e12 / peak_tf if times["spike_fwd_bwd"] > 0 else None,
+        "note": "direct_equivalent_frac > 1 means the stage finishes faster than the FP64 pipe could evaluate every (spike, "
+                "latent, inducing point) kernel value: the panel path evaluates kernels at NB nodes per trial instead of "
+                "S_r spikes (include/svgpfa_b200.h); the round-1 direct kernel ran this stage at 0.69",
+        "hbm_bytes_panel_moments": 2.0 * 8.0 * Rl * N_ * NB if panel else 0.0,
+        "hbm_frac": (2.0 * 8.0 * Rl * N_ * NB / times["spike_fwd_bwd"] / 1e9 / hbm_peak_gbs()) if panel and times["spike_fwd_bwd"] > 0 else None}
+    try:        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per trial x trials)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        per_trial = tr.get(args.config, {}).get(dom)
+        if per_trial:
+            roofline["traffic"] = per_trial["dram_bytes_per_trial"] * Rl
+            roofline["traffic_note"] = per_trial.get("note", "")
     except Exception:
         pass
 

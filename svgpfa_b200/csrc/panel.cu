@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims 
         for (int a = 0; a < KT; ++a)
 #pragma unroll
             for (int c = 0; c < NCT; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
-#pragma unroll 4
-        for (int ks = 0; ks < N4 / 4; ++ks) {
+#pragma unroll 8
+        for (int ks = 0; ks < N4 / 4; ++ks) {              // deep unrolling = tau loads in flight (ncu: long-scoreboard 15)
             const int n = 4 * ks + tg;
             double b[NCT], a[KT];
 #pragma unroll
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, s
             const int n = row0 + 8 * t + g;
             if (row0 + 8 * t >= N) break;                 // warp-uniform
             const double* tau = bf.pm_tau + ((size_t)r * N + (n < N ? n : N - 1)) * NB + tg;
-#pragma unroll 8
-            for (int ks = 0; ks < NB / 4; ++ks) {
+#pragma unroll 16
+            for (int ks = 0; ks < NB / 4; ++ks) {          // 16 tau loads in flight per lane (ncu: long-scoreboard 25)
                 const double a = n < N ? __ldg(tau + 4 * ks) : 0.0;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt)
@@ -343,7 +343,7 @@ int launch_dC(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t s
     const int NB = dims->pm_B * PM_P;
     const size_t smem = sizeof(double) * (size_t)8 * KT * (NB + 4);
     const int nblk = (dims->N + PMD_ROWS - 1) / PMD_ROWS, nt = svgpfa_ntrials(dims);
-    int gy = (2 * svgpfa_sm_count() + nblk - 1) / nblk;
+    int gy = (3 * svgpfa_sm_count() + nblk - 1) / nblk;      // three resident CTAs per SM (registers)
     if (gy > nt) gy = nt;
     SVGPFA_ENSURE_SMEM(smem, panel_dC_kernel<KT>);
     panel_dC_kernel<KT><<<dim3(nblk, gy), PMG_THREADS, smem, st>>>(*dims, *buf);
