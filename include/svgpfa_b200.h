@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 4
+#define SVGPFA_ABI_VERSION 5
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -154,6 +154,8 @@ typedef struct svgpfa_buffers {
     double* pm_mt;               /* R*K*NB   [r][k][i]  node weights  sum_n C[n,k] tau[r][n][i]                        */
     /* ---- cached-statistics path (embedding M-step) -------------------------------------- */
     double* mu_s;                /* S*K   latent means at spike times, [s][k]                   */
+    double* gsum;                /* N*K   sum over the shard's spikes of neuron n of mu_s[s][k]: with cached statistics the
+                                    spike part of the ELL is sum_{n,k} gsum[n][k] C[n][k], linear in C                */
     /* ---- outputs ------------------------------------------------------------------------ */
     double* shared;              /* SVGPFA_SHARED_HDR + N*K + N + TH: [elbo, ell, kl, term1, term2, status, r, k | dC | dd | dtheta]
                                     -- the buffer a multi-GPU caller all-reduces; status/r/k = info[0..2]
@@ -212,8 +214,11 @@ int svgpfa_spike_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uin
  *   svgpfa_panel_moments       : pm_tau from spike_t / seg_off for the trial range (static: once per data set and
  *                                panelisation)
  *   svgpfa_spike_panel_fwd_bwd : pm_mun (latent means at the nodes), pm_mt = C^T tau, dC += tau mun^T, then abar_spk,
- *                                dz_acc, dth_part from the node weights -- kernel values at R*K*M*NB points */
+ *                                dz_acc, dth_part from the node weights -- kernel values at R*K*M*NB points
+ *   svgpfa_panel_neuron_sums   : gsum[n][k] = sum_{spikes of neuron n} mu_k(t_s) for the cached-statistics path
+ *                                (embedding M-step) without materialising the S x K spike-time means */
 int svgpfa_panel_moments(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+int svgpfa_panel_neuron_sums(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
 int svgpfa_spike_panel_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 
 /* (ii)+(v) adjoints through alpha, c, X, the KL term and the Cholesky factorisation: gm, gcholvec,
@@ -234,10 +239,12 @@ int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_
  *                                 (SVPosteriorOnLatentsAssocTimes.computeMeansAndVars, mean part)
  *   svgpfa_cached_ell_fwd_bwd   : ELL(C, d | mu_q, var_q, mu_s) and dC, dd into `shared`
  *                                 (PointProcessELL.evalSumAcrossTrialsAndNeurons with
- *                                  svPosteriorOnLatentsStats, expectedLogLikelihood.py:107-135);
- *                                 the spike part is the HBM-bound ragged gather over mu_s. */
+ *                                  svPosteriorOnLatentsStats, expectedLogLikelihood.py:107-135).
+ *                                 The spike part is the HBM-bound ragged gather over mu_s into gsum; it does not depend
+ *                                 on (C, d), so flags = SVGPFA_REUSE_SPIKE skips it when gsum already holds the sums of
+ *                                 these statistics (every closure evaluation of an embedding M-step after the first). */
 int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
-int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 
 /* Host helper: (r,n) segment offsets from per-segment spike counts, and the per-spike neuron index the
  * reference builds (expectedLogLikelihood.py:168-172), for the bit-exact indexing check.

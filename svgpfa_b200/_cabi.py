@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -42,7 +42,7 @@ class Dims(C.Structure):
 BUFFER_FIELDS = (
     "desc", "kscale", "theta", "Z", "m", "cholvec", "C", "d", "tq", "wq", "spike_t", "seg_off", "spike_cnt",
     "L", "Li", "X", "c", "alpha", "logdetL", "kl_rk", "A_q", "abar_q", "abar_spk", "dz_acc", "dth_part",
-    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "pm_tau", "pm_mun", "pm_mt", "mu_s",
+    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "pm_tau", "pm_mun", "pm_mt", "mu_s", "gsum",
     "shared", "gZ", "gm", "gcholvec", "info")
 
 
@@ -71,12 +71,13 @@ SYMBOLS = {
     "svgpfa_quad_latent_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_spike_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_panel_moments": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
+    "svgpfa_panel_neuron_sums": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_spike_panel_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_indpoints_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_finalize": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_elbo_grad": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_spike_latent_means": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
-    "svgpfa_cached_ell_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
+    "svgpfa_cached_ell_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_build_segments_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgpfa_elbo_grad_host": (C.c_int, [_P(Dims), _P(Buffers), _P(HostIO), C.c_uint32, C.c_void_p]),
     "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),

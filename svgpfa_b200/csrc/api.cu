@@ -6,7 +6,7 @@
 
 #include "common.cuh"
 
-int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t stream);
+int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, bool reuse, cudaStream_t stream);
 
 namespace {
 
@@ -236,7 +236,7 @@ extern "C" int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* b
     return rc;
 }
 
-extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
+extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     int rc = check_dims(dims, buf, "cached_ell_fwd_bwd");
     if (rc) return rc;
     if (!buf->fin_part) return svgpfa_set_error(SVGPFA_E_ARG, "cached_ell_fwd_bwd: fin_part", cudaSuccess);
@@ -247,7 +247,7 @@ extern "C" int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_b
     zl.p[1] = buf->term1_part; zl.n[1] = SVGPFA_TERM1_SLOTS;
     zero_kernel<<<8, 256, 0, st>>>(zl);
     rc = svgpfa_quad_embed_fwd_bwd(dims, buf, SVGPFA_GRAD_EMBEDDING, stream); if (rc) return rc;
-    rc = svgpfa_launch_spike_gather(dims, buf, st); if (rc) return rc;
+    rc = svgpfa_launch_spike_gather(dims, buf, (flags & SVGPFA_REUSE_SPIKE) != 0, st); if (rc) return rc;
     // term1 and the d part of term2; no KL, no alpha.abar (the gather produced the C part in shared[4])
     svgpfa_dims d0 = *dims;
     d0.R = 0;                                   // empties the kl_rk loop; the alpha.abar loop is off (use_abar = 0)

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims 
 constexpr int PMD_ROWS = 256;
 
 template <int KT>
-__global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
+__global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, svgpfa_buffers bf, double* __restrict__ gC) {
     extern __shared__ double pd_sm[];                     // mun of one trial, [8 KT][NB + 4], rows >= K zero
     const int N = dm.N, K = dm.K, NB = dm.pm_B * PM_P, LDM = NB + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, s
             }
         }
     }
-    double* gC = bf.shared + SVGPFA_SHARED_HDR;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int n = row0 + 8 * t + g;
@@ -339,15 +338,25 @@ int launch_weights(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStrea
 }
 
 template <int KT>
-int launch_dC(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t st) {
+int launch_dC(const svgpfa_dims* dims, const svgpfa_buffers* buf, double* out, cudaStream_t st) {
     const int NB = dims->pm_B * PM_P;
     const size_t smem = sizeof(double) * (size_t)8 * KT * (NB + 4);
     const int nblk = (dims->N + PMD_ROWS - 1) / PMD_ROWS, nt = svgpfa_ntrials(dims);
     int gy = (3 * svgpfa_sm_count() + nblk - 1) / nblk;      // three resident CTAs per SM (registers)
     if (gy > nt) gy = nt;
     SVGPFA_ENSURE_SMEM(smem, panel_dC_kernel<KT>);
-    panel_dC_kernel<KT><<<dim3(nblk, gy), PMG_THREADS, smem, st>>>(*dims, *buf);
+    panel_dC_kernel<KT><<<dim3(nblk, gy), PMG_THREADS, smem, st>>>(*dims, *buf, out);
     return SVGPFA_OK;
+}
+
+int launch_dC_any(const svgpfa_dims* dims, const svgpfa_buffers* buf, double* out, cudaStream_t st) {
+    switch ((dims->K + 7) / 8) {
+        case 1: return launch_dC<1>(dims, buf, out, st);
+        case 2: return launch_dC<2>(dims, buf, out, st);
+        case 3: return launch_dC<3>(dims, buf, out, st);
+        case 4: return launch_dC<4>(dims, buf, out, st);
+        default: return launch_dC<5>(dims, buf, out, st);
+    }
 }
 
 bool panel_args_ok(const svgpfa_dims* d, const svgpfa_buffers* b) {
@@ -370,6 +379,23 @@ extern "C" int svgpfa_panel_moments(const svgpfa_dims* dims, const svgpfa_buffer
     const size_t smem = sizeof(double) * PMK_WARPS * 2 * NB;
     panel_moments_kernel<<<(unsigned)(nt * n_chunks), 32 * PMK_WARPS, smem, (cudaStream_t)stream>>>(*dims, *buf, (int)n_chunks, chunk);
     SVGPFA_CHECK_LAUNCH("panel_moments");
+    return SVGPFA_OK;
+}
+
+// gsum[n][k] = sum over the shard's spikes of neuron n of the latent mean mu_k(t_s), through the panel moments: what the
+// cached-statistics path needs from the spike times (see spike_gather_kernel in spike.cu) without the S x K array.
+extern "C" int svgpfa_panel_neuron_sums(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
+    if (!panel_args_ok(dims, buf) || !buf->pm_mun || !buf->gsum)
+        return svgpfa_set_error(SVGPFA_E_ARG, "panel_neuron_sums", cudaSuccess);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(buf->gsum, 0, sizeof(double) * (size_t)dims->N * dims->K, st);
+    const int nt = svgpfa_ntrials(dims);
+    if (nt == 0 || dims->N == 0) return SVGPFA_OK;
+    panel_nodal_means_kernel<<<dim3(nt, dims->K), PMN_THREADS, 0, st>>>(*dims, *buf);
+    SVGPFA_CHECK_LAUNCH("panel_nodal_means");
+    const int rc = launch_dC_any(dims, buf, buf->gsum, st);
+    if (rc) return rc;
+    SVGPFA_CHECK_LAUNCH("panel_dC (neuron sums)");
     return SVGPFA_OK;
 }
 
@@ -398,13 +424,7 @@ extern "C" int svgpfa_spike_panel_fwd_bwd(const svgpfa_dims* dims, const svgpfa_
     if (rc) return rc;
     SVGPFA_CHECK_LAUNCH("panel_weights");
     if (need_emb) {
-        switch (KT) {
-            case 1: rc = launch_dC<1>(dims, buf, st); break;
-            case 2: rc = launch_dC<2>(dims, buf, st); break;
-            case 3: rc = launch_dC<3>(dims, buf, st); break;
-            case 4: rc = launch_dC<4>(dims, buf, st); break;
-            default: rc = launch_dC<5>(dims, buf, st); break;
-        }
+        rc = launch_dC_any(dims, buf, buf->shared + SVGPFA_SHARED_HDR, st);
         if (rc) return rc;
         SVGPFA_CHECK_LAUNCH("panel_dC");
     }

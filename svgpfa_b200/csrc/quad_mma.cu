@@ -530,7 +530,6 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
                     am[qt] = muT[(4 * ks + tg) * LDQ + 8 * qt + g];
                     av[qt] = varT[(4 * ks + tg) * LDQ + 8 * qt + g];
                 }
-#pragma unroll
                 double bc2[2];
 #pragma unroll
                 for (int nl = 0; nl < 2; ++nl) {

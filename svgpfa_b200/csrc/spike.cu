@@ -458,43 +458,69 @@ __global__ void __launch_bounds__(SM_THREADS) spike_means_kernel(svgpfa_dims dm,
 }
 
 // ------------------------------------------------------------------------------------------
-// One warp per (trial, neuron) segment; lane <-> latent (K <= 32 per pass); 4 spike rows in flight.
+// Ragged gather of the cached-statistics path: gsum[n][k] += sum_{s in (r,n)} mu_s[s][k] over the shard's trials.
+// The rows of one (trial, neuron) segment are contiguous in mu_s ([s][k]), so a segment is a contiguous block of
+// cnt*K doubles.  One warp per segment; lane = (row, latent) with 32 / K rows per pass (K = 20: 20 lanes, K = 3:
+// 30 lanes -- the round-1 mapping lane <-> latent left 3 of 32 lanes busy there), four passes in flight; the lanes of
+// one latent are joined through shuffles at the end of the segment.  HBM-bound: S*K*8 bytes are read once.
+// With the statistics cached the spike part of the expected log-likelihood is LINEAR in C,
+//     sum_s sum_k mu_s[s][k] C[n_s][k] = sum_{n,k} gsum[n][k] C[n][k],
+// so the gather runs once per embedding M-step (svgpfa_cached_ell_fwd_bwd with SVGPFA_REUSE_SPIKE skips it) and every
+// closure evaluation after the first costs N*K multiply-adds for this term.
 constexpr int SG_THREADS = 256;
 
 __global__ void __launch_bounds__(SG_THREADS) spike_gather_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
-    __shared__ double red[32];
     const int lane = threadIdx.x & 31;
     const int wpb = SG_THREADS / 32;
     const int64_t seg0 = (int64_t)dm.r0 * dm.N, nseg = seg0 + (int64_t)(dm.rn ? dm.rn : dm.R) * dm.N;
     const int K = dm.K;
-    double* gC = bf.shared + SVGPFA_SHARED_HDR;
-    double val = 0.0;
+    const int kp = K < 32 ? K : 32;                        // latents per pass
+    const int rows = 32 / kp;                              // spike rows per pass
+    const int row = lane / kp, kl = lane - row * kp;
+    const bool live = row < rows;
     for (int64_t sg = seg0 + (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); sg < nseg; sg += (int64_t)gridDim.x * wpb) {
         const int64_t s0 = bf.seg_off[sg], s1 = bf.seg_off[sg + 1];
         if (s0 == s1) continue;
         const int n = (int)(sg % dm.N);
         for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + lane;
-            if (k < K) {
-                const double* p = bf.mu_s + (size_t)s0 * K + k;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int64_t s = s0;
-                for (; s + 4 <= s1; s += 4) {
+            const int k = k0 + kl;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (live && k < K) {
+                const double* p = bf.mu_s + (size_t)(s0 + row) * K + k;
+                const size_t step = (size_t)rows * K;
+                int64_t s = s0 + row;
+                for (; s + 3 * rows < s1; s += 4 * rows) {
                     a0 += p[0];
-                    a1 += p[K];
-                    a2 += p[2 * (size_t)K];
-                    a3 += p[3 * (size_t)K];
-                    p += 4 * (size_t)K;
+                    a1 += p[step];
+                    a2 += p[2 * step];
+                    a3 += p[3 * step];
+                    p += 4 * step;
                 }
-                for (; s < s1; ++s) { a0 += *p; p += K; }
-                const double sum = (a0 + a1) + (a2 + a3);
-                atomicAdd(gC + (size_t)n * K + k, sum);
-                val = fma(sum, bf.C[(size_t)n * K + k], val);
+                for (; s < s1; s += rows) { a0 += *p; p += step; }
             }
+            double sum = (a0 + a1) + (a2 + a3);
+            for (int rr = 1; rr < rows; ++rr) {            // join the rows of one latent: lane kl collects lanes kl + rr*kp
+                const double o = __shfl_sync(0xffffffffu, sum, (kl + rr * kp) & 31);
+                if (row == 0) sum += o;
+            }
+            if (row == 0 && k < K) atomicAdd(bf.gsum + (size_t)n * K + k, sum);
         }
     }
+}
+
+// shared[4] += sum_{n,k} gsum[n][k] C[n][k];  dC += gsum          (one block; N*K is small)
+__global__ void __launch_bounds__(256) gsum_apply_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
+    __shared__ double red[32];
+    double* gC = bf.shared + SVGPFA_SHARED_HDR;
+    double val = 0.0;
+    const int NK = dm.N * dm.K;
+    for (int i = threadIdx.x; i < NK; i += blockDim.x) {
+        const double g = bf.gsum[i];
+        val = fma(g, bf.C[i], val);
+        gC[i] += g;                                        // the quadrature kernel's atomics on dC are complete (stream order)
+    }
     const double tot = block_sum(val, red);
-    if (threadIdx.x == 0) atomicAdd(bf.shared + 4, tot);     // term2 (the d part is added by finalize)
+    if (threadIdx.x == 0) bf.shared[4] += tot;             // term2 (the d part is added by finalize)
 }
 
 }  // namespace
@@ -576,13 +602,21 @@ extern "C" int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_b
     return SVGPFA_OK;
 }
 
-int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t stream) {
-    if (dims->R == 0 || dims->S == 0) return SVGPFA_OK;
-    const int nsm = svgpfa_sm_count();
-    const long nseg = (long)svgpfa_ntrials(dims) * dims->N;
-    long blocks = (nseg + SG_THREADS / 32 - 1) / (SG_THREADS / 32);
-    if (blocks > (long)nsm * 16) blocks = (long)nsm * 16;
-    spike_gather_kernel<<<(unsigned)blocks, SG_THREADS, 0, stream>>>(*dims, *buf);
-    SVGPFA_CHECK_LAUNCH("spike_gather");
+int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, bool reuse, cudaStream_t stream) {
+    if (!buf->gsum) return svgpfa_set_error(SVGPFA_E_ARG, "cached_ell_fwd_bwd: gsum", cudaSuccess);
+    if (dims->N == 0) return SVGPFA_OK;
+    if (!reuse) {
+        cudaMemsetAsync(buf->gsum, 0, sizeof(double) * (size_t)dims->N * dims->K, stream);
+        if (dims->R > 0 && dims->S > 0) {
+            const int nsm = svgpfa_sm_count();
+            const long nseg = (long)svgpfa_ntrials(dims) * dims->N;
+            long blocks = (nseg + SG_THREADS / 32 - 1) / (SG_THREADS / 32);
+            if (blocks > (long)nsm * 16) blocks = (long)nsm * 16;
+            spike_gather_kernel<<<(unsigned)blocks, SG_THREADS, 0, stream>>>(*dims, *buf);
+            SVGPFA_CHECK_LAUNCH("spike_gather");
+        }
+    }
+    gsum_apply_kernel<<<1, 256, 0, stream>>>(*dims, *buf);
+    SVGPFA_CHECK_LAUNCH("gsum_apply");
     return SVGPFA_OK;
 }

@@ -108,8 +108,36 @@ class _LowerBoundFn(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class _LazySpikeMeans:
+    """Per-trial (S_r, K) latent means at the spike times, computed on first access (sequence protocol of the list
+    the reference returns, expectedLogLikelihood.py:141-147).  Valid while the model's parameters are the ones the
+    statistics were computed for."""
+
+    def __init__(self, model, offsets, snapshot):
+        self._model, self._off, self._snapshot, self._rows = model, offsets, snapshot, None
+
+    def _materialise(self):
+        if self._rows is None:
+            if self._model._param_snapshot() != self._snapshot:
+                raise RuntimeError("the spike-time means of these statistics were not materialised before the model's "
+                                   "parameters changed; read stats['assocTimes'][0] right after computing the statistics")
+            mu_s = self._model._spike_time_means()
+            self._rows = [mu_s[self._off[r]:self._off[r + 1]] for r in range(len(self._off) - 1)]
+        return self._rows
+
+    def __len__(self):
+        return len(self._off) - 1
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+
 class B200SVLowerBound:
     _PENDING_SLOTS = 8
+    _stats_serial = 0
 
     def __init__(self, kernels=None, device=None, process_group=None, check_errors=True, shard_mode="auto"):
         self._device = torch.device(device) if device is not None else None
@@ -126,6 +154,7 @@ class B200SVLowerBound:
         self._quad_warps = 0               # tuning: warps per CTA of the quadrature kernels (0 = automatic)
         self.spike_method = "auto"         # "auto" | "direct" | "panel": how the spike-time term is evaluated
         self._pm = None                    # state of the panel path: dict(B, lo, w, theta_version, built)
+        self._gsum_key = None              # which cached spike-time means the per-neuron sums in `gsum` belong to
         self._kernels = None
         self._reg = None
         self._params_set = False
@@ -353,6 +382,7 @@ class B200SVLowerBound:
             varbar_part=e(n_ntiles * R * Q * K),
             term1_part=torch.zeros(_cabi.TERM1_SLOTS, dtype=_F64, device=dev),
             fin_part=torch.zeros(3 * _cabi.FIN_SLOTS, dtype=_F64, device=dev),
+            gsum=torch.zeros(max(N * K, 1), dtype=_F64, device=dev),
             info=torch.zeros(4, dtype=torch.int32, device=dev))
         self._ws = ws
         self._shared_len = _cabi.SHARED_HDR + N * K + N + self._TH
@@ -370,9 +400,11 @@ class B200SVLowerBound:
         for name, t in ws.items():
             setattr(b, name, ptr(t))
         b.mu_s = None
+        b.gsum = ptr(ws["gsum"])
         b.pm_tau = b.pm_mun = b.pm_mt = None
         self._bufs = b
         self._pm = None
+        self._gsum_key = None
         self._ready = True
         self._kzz_key = self._spike_key = None
 
@@ -625,14 +657,31 @@ class B200SVLowerBound:
         return float(io["shared"][0]), h2d, d2h
 
     # ------------------------------------------------------------------ embedding M-step (svEM.py:225-232)
+    def _spike_time_means(self):
+        """(S, K) latent means at the spike times for the CURRENT parameters (direct kernel evaluations)."""
+        dev = self._dev()
+        b = _cabi.Buffers.from_buffer_copy(self._bufs)
+        mu_s = torch.empty(max(self._S, 1) * self._K, dtype=_F64, device=dev)
+        b.mu_s = mu_s.data_ptr()
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().svgpfa_spike_latent_means(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+        return mu_s[:self._S * self._K].view(self._S, self._K)
+
     def computeSVPosteriorOnLatentsStats(self):
         """Latent posterior statistics at quadrature points (mean, var: (R,Q,K)) and at spike times
         (mean only: the exponential link never reads the variance).  Layout follows
-        expectedLogLikelihood.py:141-147; the per-trial spike tensors are views of one (S,K) buffer."""
+        expectedLogLikelihood.py:141-147; the per-trial spike tensors are views of one (S,K) buffer.
+
+        With cached statistics the spike part of the expected log-likelihood is linear in C with coefficients
+        G[n,k] = sum over the spikes of neuron n of mu_k(t_s); when the panel path is active G comes straight from the
+        panel moments and the (S,K) array (33 GB at config #5) is only built if somebody reads it
+        (``stats["assocTimes"][0]`` is then a lazy sequence)."""
         self._prepare()
+        self._select_spike_method()
         dev = self._dev()
         b, lib = self._bufs, _cabi.lib()
         kz_key = self._param_versions()
+        panel = self._dims.spike_method == _cabi.SPIKE_PANEL
         with torch.cuda.device(dev):
             if self._kzz_key != kz_key:
                 self._ws["info"].zero_()
@@ -640,18 +689,29 @@ class B200SVLowerBound:
                 self._kzz_key = kz_key
             _cabi.check(lib.svgpfa_indpoints_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
             _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
-            mu_s = torch.empty(max(self._S, 1) * self._K, dtype=_F64, device=dev)
-            b.mu_s = mu_s.data_ptr()
-            _cabi.check(lib.svgpfa_spike_latent_means(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+            if panel:
+                _cabi.check(lib.svgpfa_panel_neuron_sums(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
         R, Q, K = self._R, self._Q, self._K
         mu_q = self._ws["mu_q"].view(R, Q, K).clone()
         var_q = self._ws["var_q"].view(R, Q, K).clone()
-        mu_s = mu_s[:self._S * K].view(self._S, K)
-        off = self._seg_off[::self._N].cpu().tolist() if self._N else [0] * (R + 1)
-        means = [mu_s[off[r]:off[r + 1]] for r in range(R)]
         if self._check_errors and int(self._ws["info"][0].item()) == _cabi.INFO_NOT_PD:
             raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
-        return {"allTimes": (mu_q, var_q), "assocTimes": (means, [None] * R), "_b200_mu_s": mu_s}
+        B200SVLowerBound._stats_serial += 1
+        serial = B200SVLowerBound._stats_serial
+        stats = {"allTimes": (mu_q, var_q), "_b200_id": serial}
+        off = self._seg_off[::self._N].cpu().tolist() if self._N else [0] * (R + 1)
+        if panel:
+            stats["_b200_gsum"] = self._ws["gsum"].clone()
+            self._gsum_key = (serial, None)
+            stats["assocTimes"] = (_LazySpikeMeans(self, off, self._param_snapshot()), [None] * R)
+        else:
+            mu_s = self._spike_time_means()
+            stats["_b200_mu_s"] = mu_s
+            stats["assocTimes"] = ([mu_s[off[r]:off[r + 1]] for r in range(R)], [None] * R)
+        return stats
+
+    def _param_snapshot(self):
+        return (self._Zbuf._version, self._thbuf._version, self._mbuf._version, self._reg)
 
     def evalELLSumAcrossTrialsAndNeurons(self, svPosteriorOnLatentsStats=None):
         """Expected log-likelihood only (no KL).  With cached statistics it is a function of (C, d)
@@ -664,18 +724,31 @@ class B200SVLowerBound:
     def _run_cached(self, stats):
         dev = self._dev()
         mu_q, var_q = stats["allTimes"]
-        mu_s = stats.get("_b200_mu_s")
-        if mu_s is None:
-            mu_s = torch.cat([self._to_dev(x) for x in stats["assocTimes"][0]], 0)
         mu_q = self._to_dev(mu_q).contiguous()
         var_q = self._to_dev(var_q).contiguous()
-        mu_s = self._to_dev(mu_s).contiguous()
         b = _cabi.Buffers.from_buffer_copy(self._bufs)
         shared = torch.empty(self._shared_len, dtype=_F64, device=dev)
-        b.shared, b.mu_q, b.var_q, b.mu_s = shared.data_ptr(), mu_q.data_ptr(), var_q.data_ptr(), mu_s.data_ptr()
+        b.shared, b.mu_q, b.var_q = shared.data_ptr(), mu_q.data_ptr(), var_q.data_ptr()
+        # the per-neuron sums of the spike-time means do not depend on (C, d): gathered once per set of statistics
+        serial = stats.get("_b200_id")            # a serial number, not an address: addresses are reused by the allocator
+        gsum, mu_s = stats.get("_b200_gsum"), None
+        if gsum is not None:                      # panel path: the sums came with the statistics
+            key = (serial, None)
+            if self._gsum_key != key:
+                self._ws["gsum"].copy_(gsum)
+            flags = _cabi.REUSE_SPIKE
+        else:
+            mu_s = stats.get("_b200_mu_s")
+            if mu_s is None:
+                mu_s = torch.cat([self._to_dev(x) for x in stats["assocTimes"][0]], 0)
+            mu_s = self._to_dev(mu_s).contiguous()
+            b.mu_s = mu_s.data_ptr()
+            key = None if serial is None else (serial, mu_s._version)
+            flags = _cabi.REUSE_SPIKE if (key is not None and self._gsum_key == key) else 0
         with torch.cuda.device(dev):
-            _cabi.check(_cabi.lib().svgpfa_cached_ell_fwd_bwd(ctypes.byref(self._dims), ctypes.byref(b),
+            _cabi.check(_cabi.lib().svgpfa_cached_ell_fwd_bwd(ctypes.byref(self._dims), ctypes.byref(b), flags,
                                                               self._stream()), "cached_ell_fwd_bwd")
+        self._gsum_key = key
         self._finish(shared, _cabi.GRAD_EMBEDDING)
         self._cached_keepalive = (mu_q, var_q, mu_s)
         return shared
@@ -720,7 +793,7 @@ class B200SVLowerBound:
     # the kernel objects' parameter tensors, which alias the same packed buffer -- are NOT part of the state: they
     # are rebuilt from the packed buffers on load, with their requires_grad flags.
     _TRANSIENT = ("_bufs", "_dims", "_desc_host", "_desc_dev", "_ws", "_cached_keepalive", "_pg", "_Z", "_m", "_cv",
-                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared", "_pm")
+                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared", "_pm", "_gsum_key")
 
     def __getstate__(self):
         self._poll_errors(block=True)
@@ -749,6 +822,7 @@ class B200SVLowerBound:
         self._leaf_list = None
         self._last_shared = None
         self._pm = None
+        self._gsum_key = None
         if kernels is not None:
             self._kernels = []
             for cls, kst in kernels:

@@ -162,3 +162,36 @@ def test_host_buffer_entry_rebuilds_panels():
     for nb in (1, 3):
         elbo, _, _ = model.evalAndGradHost(io, copy_static=True, n_blocks=nb)
         assert abs(elbo - want) <= 1e-11 * abs(want)
+
+
+def test_cached_statistics_through_the_panel_moments():
+    """Embedding M-step (svEM.py:225-232) with the panel path active: the per-neuron sums of the spike-time means come
+    from the panel moments (no (S, K) array is built), the cached ELL and its (C, d) gradients equal the direct path,
+    and the spike-time means are still available on demand."""
+    from svgpfa_b200.testing import model_from_case, set_requires_grad
+    cfg = dict(synthetic.CONFIGS["config4"], R=5, N=50)
+    case = synthetic.make_case(cfg, seed=8)
+    res = {}
+    for method in ("direct", "panel"):
+        model = model_from_case(case, spike_method=method)
+        set_requires_grad(model, posterior=False, embedding=True, kernels=False, indlocs=False)
+        stats = model.computeSVPosteriorOnLatentsStats()
+        assert ("_b200_gsum" in stats) == (method == "panel")
+        vals = []
+        for rep in range(3):                        # later closures reuse the per-neuron sums
+            for p in model.getSVEmbeddingParams():
+                p.grad = None
+            v = model.evalELLSumAcrossTrialsAndNeurons(svPosteriorOnLatentsStats=stats)
+            (-v).backward()
+            vals.append(v.item())
+            with torch.no_grad():
+                model.getSVEmbeddingParams()[0].mul_(1.01)       # what the optimiser does between closures
+        C, d = model.getSVEmbeddingParams()
+        res[method] = (vals, C.grad.cpu().numpy(), d.grad.cpu().numpy(),
+                       torch.cat(list(stats["assocTimes"][0]), 0).cpu().numpy())
+    for a, b in zip(res["direct"][0], res["panel"][0]):
+        assert abs(a - b) <= 1e-12 * abs(a)
+    assert rel_err(res["panel"][1], res["direct"][1]) <= 1e-11
+    assert rel_err(res["panel"][2], res["direct"][2]) <= 1e-11
+    assert rel_err(res["panel"][3], res["direct"][3]) <= 1e-13
+    assert res["direct"][0][0] != res["direct"][0][1]
