@@ -246,6 +246,16 @@ int svgpfa_elbo_grad(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_
 int svgpfa_spike_latent_means(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
 int svgpfa_cached_ell_fwd_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream);
 
+/* Post-fit read-outs at arbitrary times.  The latent statistics at the times come from
+ * svgpfa_quad_latent_fwd with dims.Q = number of times per trial and buffers.tq / mu_q / var_q pointing at the times and
+ * the outputs (SVPosteriorOnLatentsAllTimes.predict, svPosteriorOnLatents.py:57-77); this call turns them into
+ *   e_mean = mu C^T + d, e_var = var (C^T)^2   (LinearSVEmbeddingAllTimes.predict, svEmbedding.py:86-92)
+ *   cif    = exp(e_mean + e_var / 2)            (PointProcessELLExpLink.computeExpectedPosteriorCIFs,
+ *                                                expectedLogLikelihood.py:62-73)
+ * each (R, Q, N) row-major; any of the three outputs may be NULL. */
+int svgpfa_embed_predict(const svgpfa_dims* dims, const svgpfa_buffers* buf, double* e_mean, double* e_var, double* cif,
+                         void* stream);
+
 /* Host helper: (r,n) segment offsets from per-segment spike counts, and the per-spike neuron index the
  * reference builds (expectedLogLikelihood.py:168-172), for the bit-exact indexing check.
  * counts_host[R*N] -> seg_off_host[R*N+1]; neuron_index_host may be NULL, else S entries (int64). */

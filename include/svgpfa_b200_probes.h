@@ -27,8 +27,10 @@ int svgpfa_peak_probe(int32_t kind, int32_t blocks, int64_t iters, double* out, 
 /* y_fast[i] = the library's exp for non-positive arguments, y_ref[i] = libdevice exp(x[i]). */
 int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_ref, int64_t n, void* stream);
 
-/* y[i] = 2^(-min(w2[i], 2.61e5) / 256), the pre-scaled exponential of the spike kernel (w2 >= 0). */
-int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream);
+/* y[i] = 2^(-min(w2[i], 2.61e5) / 256), the pre-scaled exponential of the spike kernels (w2 >= 0).
+ * variant 0: degree-4 polynomial (<= 4.5e-16; what the kernels use); 3: degree-3 economised polynomial + I2F range
+ * reduction (<= 2e-14; measured 7 % faster in tools/probe_eval.py, not adopted: see spike.cu). */
+int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, int32_t variant, void* stream);
 
 #ifdef __cplusplus
 }

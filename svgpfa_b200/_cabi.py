@@ -78,6 +78,7 @@ SYMBOLS = {
     "svgpfa_elbo_grad": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_spike_latent_means": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_cached_ell_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
+    "svgpfa_embed_predict": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgpfa_build_segments_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgpfa_elbo_grad_host": (C.c_int, [_P(Dims), _P(Buffers), _P(HostIO), C.c_uint32, C.c_void_p]),
     "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),
@@ -88,7 +89,7 @@ PROBE_SYMBOLS = {
     "svgpfa_probes_last_error": (C.c_char_p, []),
     "svgpfa_peak_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "svgpfa_exp_neg_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "svgpfa_exp2m_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgpfa_exp2m_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }
 STAGES = ("kzz_chol", "indpoints_fwd", "quad_latent_fwd", "quad_embed", "quad_latent_bwd", "spike_fwd_bwd",
           "indpoints_bwd", "finalize")

@@ -182,13 +182,20 @@ __global__ void exp_eval_kernel(const double* x, double* yf, double* yr, long n)
     }
 }
 
-__global__ void exp2m_eval_kernel(const double* w2, double* y, long n) {
+__global__ void exp2m_eval_kernel(const double* w2, double* y, long n, int variant) {
     __shared__ double tab[SVGPFA_EXP2M_TAB_BYTES / 8];
     svgpfa_load_exp2m_tab(tab);
     __syncthreads();
     const unsigned lane_tab = svgpfa_exp2m_lane_tab(tab);
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        y[i] = svgpfa_exp2m(svgpfa_exp2m_clamp(w2[i]), lane_tab);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        if (variant == 3) {                       // what spike_tile_kernel evaluates: degree 3 + I2F (svgpfa_exp2m_n<., 3>)
+            double a[1] = {svgpfa_exp2m_clamp(w2[i])}, o[1];
+            svgpfa_exp2m_n<1, 3>(a, lane_tab, o);
+            y[i] = o[0];
+        } else {
+            y[i] = svgpfa_exp2m(svgpfa_exp2m_clamp(w2[i]), lane_tab);
+        }
+    }
 }
 
 }  // namespace
@@ -237,10 +244,10 @@ extern "C" int svgpfa_exp_neg_eval(const double* x, double* y_fast, double* y_re
     return SVGPFA_OK;
 }
 
-extern "C" int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, void* stream) {
+extern "C" int svgpfa_exp2m_eval(const double* w2, double* y, int64_t n, int32_t variant, void* stream) {
     if (!w2 || !y || n < 0) return probe_error("exp2m_eval", cudaSuccess);
     if (n == 0) return SVGPFA_OK;
-    exp2m_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(w2, y, (long)n);
+    exp2m_eval_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(w2, y, (long)n, (int)variant);
     { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return probe_error("exp2m_eval", e_); }
     return SVGPFA_OK;
 }

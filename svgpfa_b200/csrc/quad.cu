@@ -571,7 +571,44 @@ __global__ void __launch_bounds__(EM_THREADS, 3) quad_embed_kernel(svgpfa_dims d
     }
 }
 
+// Post-fit read-out: embedding mean / variance and expected intensity at arbitrary times from the
+// latent statistics, one thread per (trial, time, neuron); C is read through the read-only cache.
+//   e_mean = mu C^T + d, e_var = var (C^T)^2 (svEmbedding.py:80-92), cif = exp(e_mean + e_var / 2)
+//   (expectedLogLikelihood.py:62-73)
+__global__ void __launch_bounds__(256) embed_predict_kernel(svgpfa_dims dm, svgpfa_buffers bf, double* __restrict__ e_mean,
+                                                            double* __restrict__ e_var, double* __restrict__ cif) {
+    const size_t total = (size_t)dm.R * dm.Q * dm.N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t rq = idx / dm.N;
+        const int n = (int)(idx - rq * dm.N);
+        const double* mu = bf.mu_q + rq * dm.K;
+        const double* var = bf.var_q + rq * dm.K;
+        const double* c = bf.C + (size_t)n * dm.K;
+        double m = bf.d[n], v = 0.0;
+        for (int k = 0; k < dm.K; ++k) {
+            const double ck = __ldg(c + k);
+            m = fma(mu[k], ck, m);
+            v = fma(var[k], ck * ck, v);
+        }
+        if (e_mean) e_mean[idx] = m;
+        if (e_var) e_var[idx] = v;
+        if (cif) cif[idx] = exp(fma(0.5, v, m));
+    }
+}
+
 }  // namespace
+
+extern "C" int svgpfa_embed_predict(const svgpfa_dims* dims, const svgpfa_buffers* buf, double* e_mean, double* e_var,
+                                    double* cif, void* stream) {
+    if (!dims || !buf || !buf->mu_q || !buf->var_q) return svgpfa_set_error(SVGPFA_E_ARG, "embed_predict", cudaSuccess);
+    const size_t total = (size_t)dims->R * dims->Q * dims->N;
+    if (total == 0) return SVGPFA_OK;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)svgpfa_sm_count() * 16) blocks = (size_t)svgpfa_sm_count() * 16;
+    embed_predict_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*dims, *buf, e_mean, e_var, cif);
+    SVGPFA_CHECK_LAUNCH("embed_predict");
+    return SVGPFA_OK;
+}
 
 extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd", cudaSuccess);

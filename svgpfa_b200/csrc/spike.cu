@@ -146,6 +146,12 @@ __device__ __forceinline__ void eq_eval_n(const double (&t)[U], double sc, const
     svgpfa_pin(w2);
 #pragma unroll
     for (int e = 0; e < NE; ++e) wc[e] = CLAMP ? svgpfa_exp2m_clamp(w2[e]) : w2[e];
+    // Full-accuracy variant (degree 4, <= 3.5e-16).  svgpfa_exp2m_n<NE, 3> (degree-3 economised polynomial, <= 1.8e-14,
+    // + I2F range reduction) measures 35.6 -> 33.1 cycles per warp evaluation (tools/probe_eval.py) and passes every
+    // per-evaluation parity test, but it is NOT used: with it the L-BFGS replay of the reference's own example
+    // (tests/test_gpu_parity.py::test_config1_svem_replay[direct]) takes 9 instead of 10 iterations in one step -- a
+    // termination test the reference passes by 1e-14.  This kernel is the exact-replay path; the speed comes from the
+    // panel path (panel.cu).
     svgpfa_exp2m_n<NE>(wc, etab, kv);
 #pragma unroll
     for (int u = 0; u < U; ++u) {

@@ -754,38 +754,55 @@ class B200SVLowerBound:
         return shared
 
     # ------------------------------------------------------------------ post-fit read-outs
-    def predictLatents(self, times):
-        """Posterior mean and variance of the latents at ``times`` (R, T, 1)
-        (svPosteriorOnLatents.py:57-77).  Forward-only call of the quadrature kernels."""
+    def _predict(self, times, want_embedding=False, want_cif=False):
         self._prepare()
         dev = self._dev()
         t = self._to_dev(times).reshape(self._R, -1).contiguous()
         T = int(t.shape[1])
-        mu = torch.empty(self._R * T * self._K, dtype=_F64, device=dev)
-        var = torch.empty_like(mu)
+        e = lambda n: torch.empty(self._R * T * n, dtype=_F64, device=dev)
+        mu, var = e(self._K), e(self._K)
         dims = _cabi.Dims.from_buffer_copy(self._dims)
         dims.Q = T
         b = _cabi.Buffers.from_buffer_copy(self._bufs)
         b.tq, b.mu_q, b.var_q = t.data_ptr(), mu.data_ptr(), var.data_ptr()
         lib = _cabi.lib()
+        out = [mu.view(self._R, T, self._K), var.view(self._R, T, self._K)]
         with torch.cuda.device(dev):
             if self._kzz_key != self._param_versions():
+                self._ws["info"].zero_()
                 _cabi.check(lib.svgpfa_kzz_chol_fwd(ctypes.byref(self._dims), ctypes.byref(self._bufs), self._stream()))
                 self._kzz_key = self._param_versions()
             _cabi.check(lib.svgpfa_indpoints_fwd(ctypes.byref(self._dims), ctypes.byref(self._bufs), self._stream()))
             _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(dims), ctypes.byref(b), self._stream()))
-        return mu.view(self._R, T, self._K), var.view(self._R, T, self._K)
+            if want_embedding or want_cif:
+                em = e(self._N) if want_embedding else None
+                ev = e(self._N) if want_embedding else None
+                cif = e(self._N) if want_cif else None
+                ptr = lambda x: None if x is None else ctypes.c_void_p(x.data_ptr())
+                _cabi.check(lib.svgpfa_embed_predict(ctypes.byref(dims), ctypes.byref(b), ptr(em), ptr(ev), ptr(cif),
+                                                     self._stream()))
+                shape = (self._R, T, self._N)
+                out += [None if x is None else x.view(shape) for x in (em, ev, cif)]
+        if self._check_errors and int(self._ws["info"][0].item()) == _cabi.INFO_NOT_PD:
+            self._kzz_key = None
+            raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
+        return out
+
+    def predictLatents(self, times):
+        """Posterior mean and variance of the latents at ``times`` (R, T, 1), each (R, T, K)
+        (svLowerBound.py:116-117 -> svPosteriorOnLatents.py:57-77).  Forward-only call of the quadrature kernels."""
+        mu, var = self._predict(times)[:2]
+        return mu, var
 
     def predictEmbedding(self, times):
-        """Embedding mean / variance at ``times`` (svEmbedding.py:80-92)."""
-        mu, var = self.predictLatents(times)
-        C, d = self._C.detach(), self._d.detach().reshape(1, 1, -1)
-        return mu @ C.T + d, var @ (C.T ** 2)
+        """Embedding mean / variance at ``times``, each (R, T, N) (svLowerBound.py:119-120 -> svEmbedding.py:86-92)."""
+        out = self._predict(times, want_embedding=True)
+        return out[2], out[3]
 
     def computeExpectedPosteriorCIFs(self, times):
-        """exp(mean + var/2) per trial and neuron (expectedLogLikelihood.py:62-73)."""
-        e_mean, e_var = self.predictEmbedding(times)
-        cif = torch.exp(e_mean + 0.5 * e_var)
+        """exp(mean + var/2) of the embedding per trial and neuron: ``answer[r][n]`` is a (T,) tensor
+        (svLowerBound.py:64-66 -> expectedLogLikelihood.py:62-73)."""
+        cif = self._predict(times, want_cif=True)[4]
         return [[cif[r, :, n] for n in range(cif.shape[2])] for r in range(cif.shape[0])]
 
     # ------------------------------------------------------------------ pickling (svEM.py:89-92,175-181)

@@ -45,9 +45,12 @@ def test_exp_neg_accuracy():
     assert err_ref.max() <= 4e-16
 
 
-def test_exp2m_accuracy():
-    """The spike kernel's pre-scaled exponential 2^(-w2/256) vs numpy (long double) over its whole range;
-    arguments above the limit are clamped (result ~6e-308 instead of 0 or a subnormal)."""
+@pytest.mark.parametrize("variant,bound", [(0, 4.5e-16), (3, 2.2e-14)])
+def test_exp2m_accuracy(variant, bound):
+    """The spike kernels' pre-scaled exponential 2^(-w2/256) vs numpy (long double) over its whole range;
+    arguments above the limit are clamped (result ~6e-308 instead of 0 or a subnormal).  Variant 0 is what the kernels
+    use; variant 3 (degree-3 economised polynomial, maximum relative error 1.8e-14, rounded integer returned through
+    I2F) is the measured-but-not-adopted faster form (svgpfa_b200/csrc/spike.cu)."""
     from svgpfa_b200 import _cabi
     lib = _cabi.probes()
     dev = torch.device("cuda")
@@ -60,14 +63,14 @@ def test_exp2m_accuracy():
                                  dtype=torch.float64)]).to(dev)
     y = torch.empty_like(w2)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _cabi.check_probe(lib.svgpfa_exp2m_eval(w2.data_ptr(), y.data_ptr(), w2.numel(), stream))
+    _cabi.check_probe(lib.svgpfa_exp2m_eval(w2.data_ptr(), y.data_ptr(), w2.numel(), variant, stream))
     torch.cuda.synchronize()
     w2, y = w2.cpu().numpy(), y.cpu().numpy()
     inside = w2 <= 2.609e5
     truth = np.exp2(-(w2[inside].astype(np.longdouble)) / np.longdouble(256)).astype(np.float64)
     err = np.abs(y[inside] - truth) / truth
-    assert err.max() <= 4.5e-16, float(err.max())
-    assert y[w2 == 0.0][0] == 1.0
+    assert err.max() <= bound, float(err.max())
+    assert abs(y[w2 == 0.0][0] - 1.0) <= bound
     assert np.all(y[~inside] > 0.0) and np.all(y[~inside] < 1e-306)
 
 

@@ -454,3 +454,27 @@ def test_not_positive_definite_inside_an_optimiser_closure():
         float(v)                       # what LBFGS does with the closure's loss
         model.eval()                   # next closure call: the failure of the previous evaluation is raised here
     model.checkErrors()                # nothing is left pending
+
+
+@pytest.mark.parametrize("name", ["tiny_mixed", "matlab_r5", "config3_r4"])
+def test_post_fit_readouts_match_reference(name):
+    """predictLatents / predictEmbedding / computeExpectedPosteriorCIFs on a per-trial irregular,
+    unsorted time grid that is NOT the quadrature grid and reaches outside the inducing points, against the unmodified
+    reference (tests/golden/make_predict.py; svPosteriorOnLatents.py:57-77, svEmbedding.py:86-92,
+    expectedLogLikelihood.py:62-73)."""
+    from svgpfa_b200.testing import model_from_case
+    case, _ = synthetic.load_case(os.path.join(GOLDEN, name + ".npz"))
+    ref = np.load(os.path.join(GOLDEN, "predict", name + ".npz"))
+    model = model_from_case(case)
+    times = torch.from_numpy(ref["times"])
+    mu, var = model.predictLatents(times)
+    assert rel_err(mu.cpu().numpy(), ref["latent_mean"]) <= 1e-9
+    assert rel_err(var.cpu().numpy(), ref["latent_var"]) <= 1e-8
+    e_mu, e_var = model.predictEmbedding(times)
+    assert rel_err(e_mu.cpu().numpy(), ref["embedding_mean"]) <= 1e-9
+    assert rel_err(e_var.cpu().numpy(), ref["embedding_var"]) <= 1e-8
+    cifs = model.computeExpectedPosteriorCIFs(times)
+    R, T, N = ref["cif"].shape
+    assert len(cifs) == R and len(cifs[0]) == N and tuple(cifs[0][0].shape) == (T,)
+    cif = np.stack([np.stack([c.cpu().numpy() for c in trial], axis=1) for trial in cifs])
+    assert rel_err(cif, ref["cif"]) <= 1e-9
