@@ -18,15 +18,28 @@ STEP_NAMES = ("estep", "mstep_embedding", "mstep_kernels", "mstep_indpointslocs"
 LBFGS_545 = dict(max_iter=20, lr=1.0, tolerance_grad=1e-7, tolerance_change=1e-9, line_search_fn="strong_wolfe")
 
 
-def check_step_log(log, ref_rows, rel=1e-7):
-    """Same steps, same LBFGS iteration and closure-evaluation counts, same bound after every step.  The reference
-    log prints the bound with 6 decimals (5e-13 relative here)."""
+def check_step_log(log, ref_rows, rel=1e-7, exact=True, max_iter=20):
+    """Same steps, same bound after every step (the reference log prints it with 6 decimals: 5e-13 relative here) and
+    the same L-BFGS iteration / closure-evaluation counts.
+
+    ``exact=False`` (the CUDA model): the kernels accumulate with FP64 atomics, so repeated runs differ in the last bits
+    (tests/test_gpu_parity.py::test_run_to_run_reproducibility_bound), and three of the eight steps of this example stop
+    on ``tolerance_change = 1e-9`` -- a test the reference itself passes by ~1e-14 in one of them.  Those steps may
+    then take one iteration more or less; steps that run to ``max_iter`` must match exactly, and so must at least
+    six of the eight steps."""
     assert len(log) == len(ref_rows)
+    n_exact = 0
     for got, want in zip(log, ref_rows):
         it, name, bound, niter, nfeval = got
         assert (it, STEP_NAMES.index(name)) == (int(want[0]), int(want[1]))
-        assert (niter, nfeval) == (int(want[3]), int(want[4])), (got, want.tolist())
         assert bound == pytest.approx(float(want[2]), rel=rel), (got, want.tolist())
+        same = (niter, nfeval) == (int(want[3]), int(want[4]))
+        n_exact += same
+        if exact or int(want[3]) == max_iter:
+            assert same, (got, want.tolist())
+        else:
+            assert abs(niter - int(want[3])) <= 1 and abs(nfeval - int(want[4])) <= 2, (got, want.tolist())
+    assert n_exact >= len(log) - 2, n_exact
 
 
 def test_fixture_is_the_reference_smoke_test():
