@@ -148,18 +148,29 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims 
         for (int a = 0; a < KT; ++a)
 #pragma unroll
             for (int c = 0; c < NCT; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
-#pragma unroll 8
-        for (int ks = 0; ks < N4 / 4; ++ks) {              // deep unrolling = tau loads in flight (ncu: long-scoreboard 15)
-            const int n = 4 * ks + tg;
-            double b[NCT], a[KT];
+        // batches of PW k-steps: all tau loads of a batch are issued before its first mma (ncu: long-scoreboard was the top
+        // stall with the loads left to the compiler's scheduling)
+        constexpr int PW = 8;
+        for (int ks0 = 0; ks0 < N4 / 4; ks0 += PW) {
+            double b[PW][NCT];
 #pragma unroll
-            for (int c = 0; c < NCT; ++c) b[c] = n < N ? __ldg(tau + (size_t)n * NB + 8 * c) : 0.0;
+            for (int u = 0; u < PW; ++u) {
+                const int n = 4 * (ks0 + u) + tg;
 #pragma unroll
-            for (int kt = 0; kt < KT; ++kt) a[kt] = pg_sm[n * LDC + 8 * kt + g];
+                for (int c = 0; c < NCT; ++c) b[u][c] = n < N ? __ldg(tau + (size_t)n * NB + 8 * c) : 0.0;
+            }
 #pragma unroll
-            for (int kt = 0; kt < KT; ++kt)
+            for (int u = 0; u < PW; ++u) {
+                const int n = 4 * (ks0 + u) + tg;
+                if (4 * (ks0 + u) >= N4) break;            // warp-uniform
+                double a[KT];
 #pragma unroll
-                for (int c = 0; c < NCT; ++c) pm_dmma(acc[kt][c][0], acc[kt][c][1], a[kt], b[c]);
+                for (int kt = 0; kt < KT; ++kt) a[kt] = pg_sm[n * LDC + 8 * kt + g];
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                    for (int c = 0; c < NCT; ++c) pm_dmma(acc[kt][c][0], acc[kt][c][1], a[kt], b[u][c]);
+            }
         }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
@@ -209,12 +220,16 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, s
             const int n = row0 + 8 * t + g;
             if (row0 + 8 * t >= N) break;                 // warp-uniform
             const double* tau = bf.pm_tau + ((size_t)r * N + (n < N ? n : N - 1)) * NB + tg;
-#pragma unroll 16
-            for (int ks = 0; ks < NB / 4; ++ks) {          // 16 tau loads in flight per lane (ncu: long-scoreboard 25)
-                const double a = n < N ? __ldg(tau + 4 * ks) : 0.0;
+            constexpr int PW = 16;                         // tau loads in flight per lane (ncu: long-scoreboard 25 per issue)
+            for (int ks0 = 0; ks0 < NB / 4; ks0 += PW) {   // NB / 4 is a multiple of 16
+                double a[PW];
 #pragma unroll
-                for (int kt = 0; kt < KT; ++kt)
-                    pm_dmma(acc[t][kt][0], acc[t][kt][1], a, pd_sm[(8 * kt + g) * LDM + 4 * ks + tg]);
+                for (int u = 0; u < PW; ++u) a[u] = n < N ? __ldg(tau + 4 * (ks0 + u)) : 0.0;
+#pragma unroll
+                for (int u = 0; u < PW; ++u)
+#pragma unroll
+                    for (int kt = 0; kt < KT; ++kt)
+                        pm_dmma(acc[t][kt][0], acc[t][kt][1], a[u], pd_sm[(8 * kt + g) * LDM + 4 * (ks0 + u) + tg]);
             }
         }
     }
@@ -342,7 +357,7 @@ int launch_dC(const svgpfa_dims* dims, const svgpfa_buffers* buf, double* out, c
     const int NB = dims->pm_B * PM_P;
     const size_t smem = sizeof(double) * (size_t)8 * KT * (NB + 4);
     const int nblk = (dims->N + PMD_ROWS - 1) / PMD_ROWS, nt = svgpfa_ntrials(dims);
-    int gy = (3 * svgpfa_sm_count() + nblk - 1) / nblk;      // three resident CTAs per SM (registers)
+    int gy = (2 * svgpfa_sm_count() + nblk - 1) / nblk;      // one wave of two resident CTAs per SM (96 registers)
     if (gy > nt) gy = nt;
     SVGPFA_ENSURE_SMEM(smem, panel_dC_kernel<KT>);
     panel_dC_kernel<KT><<<dim3(nblk, gy), PMG_THREADS, smem, st>>>(*dims, *buf, out);
