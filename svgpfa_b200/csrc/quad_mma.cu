@@ -12,6 +12,8 @@
 // The kernel values are generated directly in B-fragment layout (no staging); V, U, W pass through a per-warp
 // shared tile only to change from accumulator layout to B-fragment layout.  Leading dimensions (36) are chosen
 // so that every fragment load/store is bank-conflict free.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -38,6 +40,12 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 // (10 500 instructions, 23 % instruction-cache stalls); the round-1 forward kernel still generated K in B-fragment
 // registers (32 inlined evaluations per pass: 16 % instruction-fetch stalls, 166 registers) and both kernels ran
 // one evaluation chain at a time ("wait" was the top stall with two resident warps per scheduler).
+// Work split over the quadrature points (round 2).  Round 1 gave every warp whole 32-point tiles: Q = 200 is 7 tiles
+// (the last one 8 points wide) over 4 warps, i.e. two passes with the fourth warp idle in the second and 24 padded
+// points -- 28 % of the tensor work wasted.  Now the points are cut into 8-point GROUPS (the n extent of one mma),
+// the groups are dealt to the warps as evenly as possible (Q = 200: 25 groups -> 7, 6, 6, 6) and a warp covers its
+// share in passes of 4 or 3 groups (7 -> 4 + 3, 6 -> 3 + 3): two instantiations of the pass body, no idle warp, at
+// most two padded groups per warp.
 template <int MT, bool BWD>
 __global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 2 : 4)
 quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
@@ -54,17 +62,17 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     const int g = lane >> 2, tg = lane & 3;
     const bool need_kz = BWD && (flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS));
     double* Lis = sm;                                   // [MP][LD]  Li
-    double* Xs = Lis + MP * LD;                         // [MP][LD]  X
+    double* Xs = Lis + MP * LD;                         // [MP][LD]  X; in the adjoint with need_kz: G = X X^T - I
     double* al = Xs + MP * LD;                          // [MP]
     double* zs = al + MP;                               // [MP]
     constexpr int WSTRIDE = (BWD ? 2 : 1) * MP * LDT + 3 * 32;
     double* wbase = zs + MP + (size_t)warp * WSTRIDE;
     double* tileV = wbase;                              // [MP][LDT]  (FWD: K, then) V, later Li^T W
-    double* tileU = wbase + (BWD ? MP * LDT : 0);       // [MP][LDT]  K, later U, later W      (BWD only)
+    double* tileU = wbase + (BWD ? MP * LDT : 0);       // [MP][LDT]  K, later W                (BWD only)
     double* tileK = BWD ? tileU : tileV;
-    double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the tile
+    double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the pass
     double* mbs = tt + 32;                              // [32] mubar
-    double* vbs = mbs + 32;                             // [32] 2 varbar
+    double* vbs = mbs + 32;                             // [32] varbar
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     if (kc.type == SVGPFA_KERNEL_PERIODIC) svgpfa_load_sincos_tab<1>(sctab);
     {
@@ -106,12 +114,55 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     double ab_own = 0.0, dz_raw = 0.0, th0_raw = 0.0, th1_raw = 0.0;
     const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
-    const int ntq = (dm.Q + 31) / 32;
-    bool first_pass = true;                       // every warp has at least one pass (nw <= ntq)
-    for (int qt0 = warp; qt0 < ntq; qt0 += nw) {
-        const int qbase = qt0 * 32;
+    bool first_pass = true;
+    if (need_kz) {
+        // G = X X^T - I in place of X (X itself is not needed by the adjoint): W = X X^T v - v = G v is ONE full product
+        // (2 MT k-steps x NQT mma per row tile) instead of U = X^T V followed by W = X U - V (two triangular ones, a tile
+        // round trip and a re-read of V between them).  Warp w computes the row tiles w, w + nw, ... into registers, all
+        // warps meet, then the tiles are written over X.  (Done here, not under the first pass's kernel evaluations: the
+        // block would be duplicated in both pass instantiations and its 2 MT^2 accumulators spill.)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        first_pass = false;
+        double gacc[MT][MT][2];                              // row tiles warp, warp + nw, ... (usually one)
+#pragma unroll
+        for (int o = 0; o < MT; ++o) {
+            const int it = warp + o * nw;
+            if (it < MT) {
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt) gacc[o][jt][0] = gacc[o][jt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double a = Xs[(8 * it + g) * LD + 4 * ks + tg];
+#pragma unroll
+                    for (int jt = 0; jt < MT; ++jt)
+                        dmma(gacc[o][jt][0], gacc[o][jt][1], a, Xs[(8 * jt + g) * LD + 4 * ks + tg]);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < MT; ++o) {
+            const int it = warp + o * nw;
+            if (it < MT) {
+#pragma unroll
+                for (int jt = 0; jt < MT; ++jt) {
+                    const int i = 8 * it + g, j = 8 * jt + 2 * tg;
+                    *reinterpret_cast<double2*>(Xs + i * LD + j) =
+                        make_double2(gacc[o][jt][0] - (i == j ? 1.0 : 0.0), gacc[o][jt][1] - (i == j + 1 ? 1.0 : 0.0));
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- one pass over NQT groups (8 NQT <= 32 points) starting at point qbase
+    auto run_pass = [&](auto nqt_tag, const int qbase, const int qend) {
+        constexpr int NQT = decltype(nqt_tag)::value;
+        constexpr int NPT = 8 * NQT;
         const int q_lane = qbase + lane;
-        const bool valid = q_lane < dm.Q;
+        const bool valid = lane < NPT && q_lane < qend;       // qend: end of this warp's share (a padded group belongs
+                                                              // to the next warp) and of the trial's points
         const double t_lane = valid ? bf.tq[(size_t)r * dm.Q + q_lane] : 0.0;
         tt[lane] = t_lane;
         if (BWD && valid) {                          // the partial sums are read after the kernel evaluations (below):
@@ -153,7 +204,8 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         }
         __syncwarp();
         if (BWD && lane < MP) {
-            // abar_j += sum_q mubar_q K[j][q], lane <-> inducing point, skewed column order (conflict free)
+            // abar_j += sum_q mubar_q K[j][q], lane <-> inducing point, skewed column order (conflict free); the
+            // columns of a 3-group pass beyond 24 hold zeros
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 2
             for (int c = 0; c < 32; c += 4) {
@@ -171,27 +223,27 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             first_pass = false;
         }
         // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]
-        double v[MT][4][2];
+        double v[MT][NQT][2];
 #pragma unroll
         for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
+            for (int qt = 0; qt < NQT; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            double b[4];
+            double b[NQT];
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) b[qt] = tileK[(4 * ks + tg) * LDT + 8 * qt + g];
+            for (int qt = 0; qt < NQT; ++qt) b[qt] = tileK[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
             for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
                 const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, b[qt]);
+                for (int qt = 0; qt < NQT; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, b[qt]);
             }
         }
-        double vv[4][2];
         if (!BWD) {
+            double vv[NQT][2];
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {
+            for (int qt = 0; qt < NQT; ++qt) {
                 vv[qt][0] = vv[qt][1] = 0.0;
 #pragma unroll
                 for (int rt = 0; rt < MT; ++rt) {
@@ -200,37 +252,33 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                 }
             }
             __syncwarp();                                            // every lane is done reading K (same tile)
-        }
 #pragma unroll
-        for (int rt = 0; rt < MT; ++rt)
+            for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt)
-                *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
-        __syncwarp();
-        // ---- U = X^T V     u[jt][qt] = U[8 jt + g][8 qt + 2 tg + {0,1}]
-        double u[MT][4][2];
-        if (!BWD || need_kz) {
+                for (int qt = 0; qt < NQT; ++qt)
+                    *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
+            __syncwarp();
+            // ---- U = X^T V     u[jt][qt] = U[8 jt + g][8 qt + 2 tg + {0,1}]
+            double u[MT][NQT][2];
 #pragma unroll
             for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) u[jt][qt][0] = u[jt][qt][1] = 0.0;
+                for (int qt = 0; qt < NQT; ++qt) u[jt][qt][0] = u[jt][qt][1] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                double b[4];
+                double b[NQT];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) b[qt] = tileV[(4 * ks + tg) * LDT + 8 * qt + g];
+                for (int qt = 0; qt < NQT; ++qt) b[qt] = tileV[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
                 for (int jt = 0; jt <= ks / 2 && jt < MT; ++jt) {    // X^T upper-triangular: k-step ks feeds row tiles <= ks/2
                     const double a = Xs[(4 * ks + tg) * LD + 8 * jt + g];
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt) dmma(u[jt][qt][0], u[jt][qt][1], a, b[qt]);
+                    for (int qt = 0; qt < NQT; ++qt) dmma(u[jt][qt][0], u[jt][qt][1], a, b[qt]);
                 }
             }
-        }
-        if (!BWD) {
             // var = s2 - ||v||^2 + ||u||^2 : column sums over the 8 row groups
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {
+            for (int qt = 0; qt < NQT; ++qt) {
                 double d0 = -vv[qt][0], d1 = -vv[qt][1];
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt) {
@@ -244,14 +292,20 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                 }
                 if (g == 0) {                                      // lanes 0..3 hold columns 8 qt + 2 tg + {0,1}
                     const int q = qbase + 8 * qt + 2 * tg;
-                    if (q < dm.Q) bf.var_q[((size_t)r * dm.Q + q) * dm.K + k] = kc.s2 + d0;
-                    if (q + 1 < dm.Q) bf.var_q[((size_t)r * dm.Q + q + 1) * dm.K + k] = kc.s2 + d1;
+                    if (q < qend) bf.var_q[((size_t)r * dm.Q + q) * dm.K + k] = kc.s2 + d0;
+                    if (q + 1 < qend) bf.var_q[((size_t)r * dm.Q + q + 1) * dm.K + k] = kc.s2 + d1;
                 }
             }
         } else {
-            // ---- A += V diag(varbar) V^T over the 32 points: k-step = 4 points, A/B fragments from the V tile
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
+            for (int rt = 0; rt < MT; ++rt)
+#pragma unroll
+                for (int qt = 0; qt < NQT; ++qt)
+                    *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
+            __syncwarp();
+            // ---- A += V diag(varbar) V^T over the points of the pass: k-step = 4 points, A/B fragments from the V tile
+#pragma unroll
+            for (int ks = 0; ks < 2 * NQT; ++ks) {
                 const double sv = vbs[4 * ks + tg];
                 double av[MT];
 #pragma unroll
@@ -263,78 +317,71 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                         dmma(accA[it * (it + 1) / 2 + jt][0], accA[it * (it + 1) / 2 + jt][1], av[it] * sv, av[jt]);
             }
             if (need_kz) {
-                __syncwarp();                                        // K (tileU) fully consumed by every lane
-#pragma unroll
-                for (int jt = 0; jt < MT; ++jt)
-#pragma unroll
-                    for (int qt = 0; qt < 4; ++qt)
-                        *reinterpret_cast<double2*>(tileU + (8 * jt + g) * LDT + 8 * qt + 2 * tg) = make_double2(u[jt][qt][0], u[jt][qt][1]);
-                __syncwarp();
-                // ---- W = X U - V   (accumulators start at -V, re-read in accumulator layout)
-                double w[MT][4][2];
+                // ---- W = G V   (G = X X^T - I, symmetric, full)
+                double w[MT][NQT][2];
 #pragma unroll
                 for (int it = 0; it < MT; ++it)
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt) {
-                        const double2 vv2 = *reinterpret_cast<const double2*>(tileV + (8 * it + g) * LDT + 8 * qt + 2 * tg);
-                        w[it][qt][0] = -vv2.x;
-                        w[it][qt][1] = -vv2.y;
-                    }
+                    for (int qt = 0; qt < NQT; ++qt) w[it][qt][0] = w[it][qt][1] = 0.0;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    double b[4];
+                    double b[NQT];
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt) b[qt] = tileU[(4 * ks + tg) * LDT + 8 * qt + g];
+                    for (int qt = 0; qt < NQT; ++qt) b[qt] = tileV[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
-                    for (int it = ks / 2; it < MT; ++it) {           // X lower-triangular
+                    for (int it = 0; it < MT; ++it) {
                         const double a = Xs[(8 * it + g) * LD + 4 * ks + tg];
 #pragma unroll
-                        for (int qt = 0; qt < 4; ++qt) dmma(w[it][qt][0], w[it][qt][1], a, b[qt]);
+                        for (int qt = 0; qt < NQT; ++qt) dmma(w[it][qt][0], w[it][qt][1], a, b[qt]);
                     }
                 }
-                __syncwarp();                                        // every lane is done reading U
+                __syncwarp();                                        // K (tileU) fully consumed by every lane (abar loop)
 #pragma unroll
                 for (int it = 0; it < MT; ++it)
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt)
+                    for (int qt = 0; qt < NQT; ++qt)
                         *reinterpret_cast<double2*>(tileU + (8 * it + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[it][qt][0], w[it][qt][1]);
                 __syncwarp();
-                // ---- Kv = Li^T W -> tileV (V is no longer needed)
+                // ---- Kv = Li^T W -> tileV (V is no longer needed once every lane is past the W product)
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt) w[jt][qt][0] = w[jt][qt][1] = 0.0;
+                    for (int qt = 0; qt < NQT; ++qt) w[jt][qt][0] = w[jt][qt][1] = 0.0;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    double b[4];
+                    double b[NQT];
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt) b[qt] = tileU[(4 * ks + tg) * LDT + 8 * qt + g];
+                    for (int qt = 0; qt < NQT; ++qt) b[qt] = tileU[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
                     for (int jt = 0; jt <= ks / 2 && jt < MT; ++jt) {    // Li^T upper-triangular
                         const double a = Lis[(4 * ks + tg) * LD + 8 * jt + g];
 #pragma unroll
-                        for (int qt = 0; qt < 4; ++qt) dmma(w[jt][qt][0], w[jt][qt][1], a, b[qt]);
+                        for (int qt = 0; qt < NQT; ++qt) dmma(w[jt][qt][0], w[jt][qt][1], a, b[qt]);
                     }
                 }
-                __syncwarp();                                        // SYRK and the W initialisation are done with V
+                // (the __syncwarp before the W store ordered every lane's V reads -- SYRK and the W product -- before here)
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
-                    for (int qt = 0; qt < 4; ++qt)
+                    for (int qt = 0; qt < NQT; ++qt)
                         *reinterpret_cast<double2*>(tileV + (8 * jt + g) * LDT + 8 * qt + 2 * tg) = make_double2(w[jt][qt][0], w[jt][qt][1]);
                 __syncwarp();
                 // ---- kbar = 2 varbar Kv + mubar alpha and its products with dkappa; lane <-> inducing point, four
-                //      points per iteration.  Raw moments only: h = kbar kappa, dz += h (delta | sin 2x),
-                //      th0 += h (delta^2 | sin^2), th1 += h sin 2x delta; the constants dd, dl, dp are applied once.
+                //      points per iteration, the NPT points of the pass in skewed order.  Raw moments only:
+                //      h = kbar kappa, dz += h (delta | sin 2x), th0 += h (delta^2 | sin^2), th1 += h sin 2x delta;
+                //      the constants dd, dl, dp are applied once at the end.
                 if (lane < M) {
 #pragma unroll 1
-                    for (int c = 0; c < 32; c += 4) {
+                    for (int c = 0; c < NPT; c += 4) {
                         double dl[4], kv[4], qq[4], s2x[4];
                         int qi[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            qi[e] = (c + e + lane) & 31;
-                            dl[e] = tt[qi[e]] - zj_own;
+                            int q = c + e + lane;
+                            if (q >= NPT) q -= NPT;
+                            if (q >= NPT) q -= NPT;
+                            qi[e] = q;
+                            dl[e] = tt[q] - zj_own;
                         }
                         kappa_vals_n<4>(kc, dl, etab, sctab, kv, qq, s2x);
 #pragma unroll
@@ -356,6 +403,22 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             }
         }
         __syncwarp();                                                // tiles are reused by the next pass
+    };
+
+    // ---- this warp's share of the 8-point groups and its passes (see above); every warp gets at least one group
+    {
+        const int G = (dm.Q + 7) / 8;
+        const int base = G / nw, rem = G - base * nw;
+        const int share = base + (warp < rem ? 1 : 0);
+        int gstart = warp * base + (warp < rem ? warp : rem);
+        const int qend = min(dm.Q, 8 * (gstart + share));
+        const int np = (share + 3) / 4;
+        int n4 = share - 3 * np;                                     // passes of four groups; the rest take three
+        if (n4 < 0) n4 = 0;
+        for (int p = 0; p < np; ++p) {
+            if (p < n4) { run_pass(std::integral_constant<int, 4>{}, 8 * gstart, qend); gstart += 4; }
+            else { run_pass(std::integral_constant<int, 3>{}, 8 * gstart, qend); gstart += 3; }
+        }
     }
     if (!BWD) return;
     // d delta / d z = -1;  dkappa/ddelta = kappa (delta | sin 2x) dd,  dkappa/dtheta0 = kappa (delta^2 | sin^2) dl,
@@ -410,7 +473,8 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
 
 template <int MT, bool BWD>
 void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
-    int nw = (dims->Q + 31) / 32;
+    const int G = (dims->Q + 7) / 8;                    // 8-point groups
+    int nw = (G + 3) / 4;                               // a warp takes up to four groups before another one is added
     int cap = dims->quad_warps > 0 ? dims->quad_warps : QM_MAX_WARPS;
     if (cap > QM_MAX_WARPS) cap = QM_MAX_WARPS;
     if (nw > cap) nw = cap;

@@ -18,15 +18,16 @@ STEP_NAMES = ("estep", "mstep_embedding", "mstep_kernels", "mstep_indpointslocs"
 LBFGS_545 = dict(max_iter=20, lr=1.0, tolerance_grad=1e-7, tolerance_change=1e-9, line_search_fn="strong_wolfe")
 
 
-def check_step_log(log, ref_rows, rel=1e-7, exact=True, max_iter=20):
+def check_step_log(log, ref_rows, rel=1e-7, exact=True):
     """Same steps, same bound after every step (the reference log prints it with 6 decimals: 5e-13 relative here) and
     the same L-BFGS iteration / closure-evaluation counts.
 
     ``exact=False`` (the CUDA model): the kernels accumulate with FP64 atomics, so repeated runs differ in the last bits
-    (tests/test_gpu_parity.py::test_run_to_run_reproducibility_bound), and three of the eight steps of this example stop
-    on ``tolerance_change = 1e-9`` -- a test the reference itself passes by ~1e-14 in one of them.  Those steps may
-    then take one iteration more or less; steps that run to ``max_iter`` must match exactly, and so must at least
-    six of the eight steps."""
+    (tests/test_gpu_parity.py::test_run_to_run_reproducibility_bound).  Three of the eight steps of this example stop on
+    ``tolerance_change = 1e-9`` -- a test the reference itself passes by ~1e-14 in one of them -- and a strong-Wolfe
+    line search can take one more or one less evaluation on a borderline curvature test.  Observed on the B200: all
+    eight steps equal in most runs, one step off by one iteration or evaluation in about one run in five.  Required:
+    every step within one iteration / two evaluations of the reference's, at least six of the eight identical."""
     assert len(log) == len(ref_rows)
     n_exact = 0
     for got, want in zip(log, ref_rows):
@@ -35,7 +36,7 @@ def check_step_log(log, ref_rows, rel=1e-7, exact=True, max_iter=20):
         assert bound == pytest.approx(float(want[2]), rel=rel), (got, want.tolist())
         same = (niter, nfeval) == (int(want[3]), int(want[4]))
         n_exact += same
-        if exact or int(want[3]) == max_iter:
+        if exact:
             assert same, (got, want.tolist())
         else:
             assert abs(niter - int(want[3])) <= 1 and abs(nfeval - int(want[4])) <= 2, (got, want.tolist())
