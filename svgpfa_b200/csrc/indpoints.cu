@@ -2,7 +2,7 @@
 // shared memory:
 //   kzz_chol_kernel       Kzz = kappa(Z,Z)+reg I, L = chol(Kzz), Li = L^-1, sum log L_ii
 //   indpoints_fwd_kernel  Ls, X = Li Ls, c = Li m, alpha = Li^T c, KL_rk
-//   indpoints_bwd_kernel  adjoints through alpha, c, X, KL and the Cholesky factorisation
+//   indpoints_bwd_mma_kernel  adjoints through alpha, c, X, KL and the Cholesky factorisation (M <= 64)
 // Reference arithmetic: stats/kernelsMatricesStore.py:107-138, utils/miscUtils.py:135-155,209-216,
 // stats/klDivergence.py:31-44; adjoints per SURVEY.md Appendix A (the reference uses autograd).
 #include "common.cuh"
@@ -10,8 +10,6 @@
 namespace {
 
 constexpr int IP_THREADS = 128;
-constexpr int IP_BWD_THREADS = 256;          // 8 warps, two 8x8 output tiles per warp and product: 2.22 (128 threads) ->
-                                             // 1.71 ms on the 2000-trial shard; 512 threads 2.47 ms
 
 __device__ __forceinline__ int ld_of(int M) { return M | 1; }   // odd leading dimension: conflict-free columns
 
@@ -302,201 +300,20 @@ __global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpf
 }
 
 // ------------------------------------------------------------------------------------------
-// C(i,j) = sum_{p in [lo,hi]} a(i,p) b(p,j) on the FP64 tensor path: 8x8 output tiles, one warp per tile,
-// k-steps of 4 (mma.sync.m8n8k4.f64: 256 FMAs for one issue slot and two operand loads).  The matrices are
-// stored full with explicit zeros outside their triangle and zero padding up to MP (multiple of 8), so a tile may
-// use the union [lo, hi] of its elements' ranges.  range(i0, j0, lo, hi) gives that union for the 8x8 tile whose
-// top-left element is (i0, j0); out(i, j, value) consumes every element.  lower_only skips tiles above the diagonal.
 __device__ __forceinline__ void dmma8(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
 
-template <class FA, class FB, class FR, class FO>
-__device__ __forceinline__ void mm_mma(int MP, bool lower_only, FA a, FB b, FR range, FO out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int g = lane >> 2, tg = lane & 3, nt = MP / 8;
-    for (int t = warp; t < nt * nt; t += nw) {
-        const int it = t / nt, jt = t - it * nt;
-        if (lower_only && jt > it) continue;
-        int lo, hi;
-        range(8 * it, 8 * jt, lo, hi);
-        double c0 = 0.0, c1 = 0.0;
-        for (int ks = lo / 4; ks <= hi / 4; ++ks) dmma8(c0, c1, a(8 * it + g, 4 * ks + tg), b(4 * ks + tg, 8 * jt + g));
-        out(8 * it + g, 8 * jt + 2 * tg, c0);
-        out(8 * it + g, 8 * jt + 2 * tg + 1, c1);
-    }
-}
-
-__global__ void __launch_bounds__(IP_BWD_THREADS) indpoints_bwd_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
-    extern __shared__ double sm[];
-    __shared__ double red[32];
-    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
-    const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, MP = round_up(M, 8), ld = MP + 4, MS = MP * ld;       // ld = 4 mod 8: conflict-free fragments
-    const bool need_post = flags & SVGPFA_GRAD_POSTERIOR;
-    const bool need_kz = flags & (SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
-    double* Lm = sm;             // L
-    double* Li = Lm + MS;        // L^-1
-    double* X = Li + MS;         // L^-1 Ls
-    double* B3 = X + MS;
-    double* B4 = B3 + MS;
-    double* B5 = B4 + MS;
-    double* al = B5 + MS;        // alpha
-    double* cv = al + MP;        // c
-    double* yv = cv + MP;        // Li abar
-    double* mb = yv + MP;        // mbar
-    double* ab = mb + MP;        // abar total
-    double* zs = ab + MP;        // z
-    const int tid = threadIdx.x, T = blockDim.x;
-    const size_t mo = (size_t)r * dm.MM + ds.mmoff, vo = (size_t)r * dm.KM + ds.moff;
-    for (int idx = tid; idx < MP * MP; idx += T) {
-        const int i = idx / MP, j = idx - i * MP;
-        const bool in = i < M && j < M;
-        const size_t gi = mo + (size_t)i * M + j;
-        Lm[i * ld + j] = in ? bf.L[gi] : 0.0;
-        Li[i * ld + j] = in ? bf.Li[gi] : 0.0;
-        X[i * ld + j] = in ? bf.X[gi] : 0.0;
-        // A_q is stored lower; mirror it
-        B3[i * ld + j] = in ? ((j <= i) ? bf.A_q[gi] : bf.A_q[mo + (size_t)j * M + i]) : 0.0;
-    }
-    const double* zg = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
-    for (int i = tid; i < MP; i += T) {
-        const bool in = i < M;
-        al[i] = in ? bf.alpha[vo + i] : 0.0;
-        cv[i] = in ? bf.c[vo + i] : 0.0;
-        ab[i] = in ? bf.abar_q[vo + i] + bf.abar_spk[vo + i] : 0.0;
-        zs[i] = in ? zg[i] : 0.0;
-    }
-    __syncthreads();
-    // y = Li abar ; cbar = y - c
-    for (int i = tid; i < MP; i += T) {
-        double s = 0.0;
-        for (int p = 0; p <= i; ++p) s += Li[i * ld + p] * ab[p];
-        yv[i] = s;
-    }
-    // Xbar = tril(2 A X) - X   -> B4      (A X)(i,j) = sum_{p >= j} A(i,p) X(p,j)
-    mm_mma(MP, false, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return X[p * ld + j]; },
-           [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
-           [&](int i, int j, double v) { B4[i * ld + j] = (j <= i) ? 2.0 * v - X[i * ld + j] : 0.0; });
-    __syncthreads();
-    // mbar = Li^T cbar
-    for (int j = tid; j < MP; j += T) {
-        double s = 0.0;
-        for (int i = j; i < MP; ++i) s += Li[i * ld + j] * (yv[i] - cv[i]);
-        mb[j] = s;
-    }
-    // T = Li^T tril(Xbar) -> B5 (full)      T(i,j) = sum_{p >= max(i,j)} Li(p,i) Xbar(p,j)
-    mm_mma(MP, false, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-           [&](int i0, int j0, int& lo, int& hi) { lo = max(i0, j0); hi = MP - 1; },
-           [&](int i, int j, double v) { B5[i * ld + j] = v; });
-    __syncthreads();
-    if (need_post) {
-        double* gm = bf.gm + (size_t)dm.R * ds.moff + (size_t)r * M;
-        for (int i = tid; i < M; i += T) gm[i] = mb[i];
-        double* gcv = bf.gcholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
-        const double* cvec = bf.cholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
-        for (int idx = tid; idx < M * M; idx += T) {
-            const int i = idx / M, j = idx - i * M;
-            if (j <= i) {
-                const int p = i * (i + 1) / 2 + j;
-                gcv[p] = B5[i * ld + j] + (i == j ? 1.0 / cvec[p] : 0.0);
-            }
-        }
-    }
-    if (!need_kz) return;
-    // B4 = X^T A      (i,j) = sum_{p >= i} X(p,i) A(p,j)
-    mm_mma(MP, false, [&](int i, int p) { return X[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
-           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-           [&](int i, int j, double v) { B4[i * ld + j] = v; });
-    __syncthreads();
-    // B3 = E2 = X (X^T A) - A   (each element of B3 is read and written by its own thread only)
-    mm_mma(MP, false, [&](int i, int p) { return X[i * ld + p]; }, [&](int p, int j) { return B4[p * ld + j]; },
-           [&](int i0, int, int& lo, int& hi) { lo = 0; hi = i0 + 7; },
-           [&](int i, int j, double v) { B3[i * ld + j] = v - B3[i * ld + j]; });
-    __syncthreads();
-    // Lbar (lower) -> B4 = -2 Li^T E2 - alpha y^T - diag(1/L_ii) - T X^T - mbar c^T      (two products)
-    mm_mma(MP, true, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B3[p * ld + j]; },
-           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-           [&](int i, int j, double v) {
-               double s = 0.0;
-               if (j <= i && i < M) {
-                   s = -2.0 * v - al[i] * yv[j] - mb[i] * cv[j];
-                   if (i == j) s -= 1.0 / Lm[i * ld + i];
-               }
-               B4[i * ld + j] = s;
-           });
-    for (int idx = tid; idx < MP * MP; idx += T) {            // the skipped upper tiles of Lbar are zero
-        const int i = idx / MP, j = idx - i * MP;
-        if ((j >> 3) > (i >> 3)) B4[i * ld + j] = 0.0;
-    }
-    __syncthreads();
-    //   (T X^T)(i,j) = sum_{p <= j} T(i,p) X(j,p)
-    mm_mma(MP, true, [&](int i, int p) { return B5[i * ld + p]; }, [&](int p, int j) { return X[j * ld + p]; },
-           [&](int, int j0, int& lo, int& hi) { lo = 0; hi = j0 + 7; },
-           [&](int i, int j, double v) { if (j <= i) B4[i * ld + j] -= v; });
-    __syncthreads();
-    // P = Phi(L^T Lbar) -> B3 lower       (i,j) = sum_{p >= i} L(p,i) Lbar(p,j)      (diagonal: P_ii = s/2, S_ii = s)
-    mm_mma(MP, true, [&](int i, int p) { return Lm[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-           [&](int i, int j, double v) { if (j <= i) B3[i * ld + j] = v; });
-    __syncthreads();
-    for (int idx = tid; idx < MP * MP; idx += T) {          // S = P + P^T
-        const int i = idx / MP, j = idx - i * MP;
-        if (j > i) B3[i * ld + j] = B3[j * ld + i];
-    }
-    __syncthreads();
-    // U1 = S Li -> B4      (i,j) = sum_{p >= j} S(i,p) Li(p,j)
-    mm_mma(MP, false, [&](int i, int p) { return B3[i * ld + p]; }, [&](int p, int j) { return Li[p * ld + j]; },
-           [&](int, int j0, int& lo, int& hi) { lo = j0; hi = MP - 1; },
-           [&](int i, int j, double v) { B4[i * ld + j] = v; });
-    __syncthreads();
-    // Kbar = 0.5 Li^T U1 -> B5      (i,j) = sum_{p >= i} Li(p,i) U1(p,j)
-    mm_mma(MP, false, [&](int i, int p) { return Li[p * ld + i]; }, [&](int p, int j) { return B4[p * ld + j]; },
-           [&](int i0, int, int& lo, int& hi) { lo = i0; hi = MP - 1; },
-           [&](int i, int j, double v) { B5[i * ld + j] = 0.5 * v; });
-    __syncthreads();
-    // dZ_i = 2 sum_j Kbar_ij dkappa/ddelta(z_i - z_j);  dtheta = sum_ij Kbar_ij dkappa/dtheta
-    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    double t0 = 0.0, t1 = 0.0;
-    double* gZ = bf.gZ + (size_t)dm.R * ds.moff + (size_t)r * M;
-    // 4 threads per row: thread (i, part) sums j = part, part+4, ... ; combined with two shuffles
-    for (int base = 0; base < M; base += T / 4) {
-        const int i = base + tid / 4, part = tid & 3;
-        double dz = 0.0;
-        if (i < M) {
-            for (int j = part; j < M; j += 4) {
-                double kv, dkd, d0, d1;
-                kappa_grad(kc, zs[i] - zs[j], kv, dkd, d0, d1);
-                const double kb = B5[i * ld + j];
-                dz += kb * dkd;
-                t0 += kb * d0;
-                t1 += kb * d1;
-            }
-        }
-        dz += __shfl_xor_sync(0xffffffffu, dz, 1);
-        dz += __shfl_xor_sync(0xffffffffu, dz, 2);
-        if (i < M && part == 0 && (flags & SVGPFA_GRAD_INDLOCS)) gZ[i] = 2.0 * dz + bf.dz_acc[vo + i];
-    }
-    if (flags & SVGPFA_GRAD_KERNEL) {
-        const double s0 = block_sum(t0, red);
-        const double s1 = block_sum(t1, red);
-        if (tid == 0) {
-            double* dth = bf.dth_part + (size_t)r * dm.TH + ds.thoff;
-            dth[0] += s0;
-            if (ds.nth > 1) dth[1] += s1;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// M <= 32: the same adjoint with compile-time shapes.  What ncu showed of the kernel above (round 1: 27 900 warp
-// instructions per matrix for ~650 DMMAs, issue slots 44 % busy, FP64 pipe 5 %): the generic lambdas cost ~40
-// instructions per mma.  Here warp `it` owns the 8-row tile `it` of every product and all its column tiles (one A
-// fragment per k-step shared by the MT column tiles), the k range of each (row, column) tile is a compile-time-unrolled
-// predicated loop, and a CTA is MT warps, so ~2.3 instructions per mma and 4-5 CTAs per SM.
-// Same algebra, same buffers and the same order of the nine products as indpoints_bwd_kernel.
+// Adjoints through alpha, c, X, the KL term and the Cholesky factorisation, nine M x M products on
+// the FP64 tensor path with compile-time shapes.  What ncu showed of the round-1 kernel (one warp per 8x8 output tile,
+// generic lambdas for the operands and the k ranges: 27 900 warp instructions per matrix for ~650 mma, issue slots 44 %
+// busy, FP64 pipe 5 %): ~40 instructions per mma.  Here warp `it` owns the 8-row tile `it` of every product and all
+// its column tiles (one A fragment per k-step shared by the MT column tiles), the k range of each (row, column) tile is
+// a compile-time-unrolled predicated loop, and a CTA is MT warps: 10 500 instructions per matrix, 4 CTAs per SM at
+// M = 32.  Matrices are stored full with explicit zeros outside their triangle and zero padding up to MP = 8 MT.
 // ------------------------------------------------------------------------------------------
 // acc(jt) = sum_{ks in [lo(jt), hi(jt)]} A(8 it + g, 4 ks + tg) B(4 ks + tg, 8 jt + g);  TA / TB: operand stored transposed
 template <int MT, bool TA, bool TB, class FR, class FO>
@@ -800,17 +617,17 @@ extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffer
 extern "C" int svgpfa_indpoints_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "indpoints_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    if (dims->Mmax <= 32) {
-        switch ((dims->Mmax + 7) / 8) {
-            case 1: launch_ipb_mma<1>(dims, buf, flags, (cudaStream_t)stream); break;
-            case 2: launch_ipb_mma<2>(dims, buf, flags, (cudaStream_t)stream); break;
-            case 3: launch_ipb_mma<3>(dims, buf, flags, (cudaStream_t)stream); break;
-            default: launch_ipb_mma<4>(dims, buf, flags, (cudaStream_t)stream); break;
-        }
-    } else {
-        const size_t smem = ip_smem(dims->Mmax, 6, 6);
-        SVGPFA_ENSURE_SMEM(smem, indpoints_bwd_kernel);
-        indpoints_bwd_kernel<<<dim3(svgpfa_ntrials(dims), dims->K), IP_BWD_THREADS, smem, (cudaStream_t)stream>>>(*dims, *buf, flags);
+    // compile-time shapes for every M <= 64 (MT = ceil(M / 8) warps per matrix; M > 32: one CTA per SM, 209 KB)
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((dims->Mmax + 7) / 8) {
+        case 1: launch_ipb_mma<1>(dims, buf, flags, st); break;
+        case 2: launch_ipb_mma<2>(dims, buf, flags, st); break;
+        case 3: launch_ipb_mma<3>(dims, buf, flags, st); break;
+        case 4: launch_ipb_mma<4>(dims, buf, flags, st); break;
+        case 5: launch_ipb_mma<5>(dims, buf, flags, st); break;
+        case 6: launch_ipb_mma<6>(dims, buf, flags, st); break;
+        case 7: launch_ipb_mma<7>(dims, buf, flags, st); break;
+        default: launch_ipb_mma<8>(dims, buf, flags, st); break;
     }
     SVGPFA_CHECK_LAUNCH("indpoints_bwd");
     return SVGPFA_OK;
