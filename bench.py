@@ -242,6 +242,36 @@ def algorithmic_counts(cfg, R, S):
     }
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process (and hence its pinned host buffers, first-touch) to the CPUs of the NUMA node its GPU hangs off.
+    With every rank on node 0 the eight ranks' host<->device copies of the e2e leg share one socket's memory
+    controllers and root complexes (round 1: e2e efficiency 0.78 at 8 GPUs).  Best effort: silently skipped when the
+    topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     import torch.distributed as dist
     from svgpfa_b200 import _cabi, synthetic
@@ -253,6 +283,7 @@ def run_b200(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     pg = None
@@ -427,6 +458,7 @@ def run_b200(args):
                "d2h_bytes_per_step": int(te[3]), "ms_per_step": float(te[0]), "wall_ms_per_step_rank0": wall_e2e,
                "params_only": {"value": 1e3 / float(te[1]), "h2d_bytes_per_step": int(te[4])},
                "unpipelined_ms_per_step": float(te[5]),
+               "numa_node_rank0": numa_node,
                "api": "svgpfa_elbo_grad_host (pinned host buffers; spikes, quadrature and parameters copied every step; "
                       "copies and kernels pipelined over blocks of trials on three streams)"}
         del io

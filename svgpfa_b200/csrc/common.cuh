@@ -317,15 +317,21 @@ __device__ __forceinline__ void kappa_grad_t(const KConst& kc, double delta, con
 // (ncu: "wait" was the top stall of both quadrature kernels).  The opaque pins keep NE chains in flight.
 // --------------------------------------------------------------------------------------------------------------
 // exp(x) for x <= 0, 64-entry table in shared memory (svgpfa_load_exp_tab64), same arithmetic as svgpfa_exp_neg64
-template <int NE>
+// ANYSIGN: arguments of either sign, clamped to [-707, 709] (exp(709) = 8.2e307; the intensity integrand of a model whose
+// rates overflow float64 is meaningless either way -- the reference would report an infinite bound).
+template <int NE, bool ANYSIGN = false>
 __device__ __forceinline__ void svgpfa_exp_neg64_n(double (&x)[NE], const double* __restrict__ tab, double (&out)[NE]) {
     const double MAGIC = 6755399441055744.0;
     double t[NE], r[NE], q[NE], T[NE];
     int n[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const unsigned hi = min((unsigned)__double2hiint(x[e]), 0xC08617FFu);          // clamp to > -707
-        x[e] = __hiloint2double((int)hi, __double2loint(x[e]));
+        if (ANYSIGN) {
+            x[e] = fmin(fmax(x[e], -707.0), 709.0);
+        } else {
+            const unsigned hi = min((unsigned)__double2hiint(x[e]), 0xC08617FFu);      // clamp to > -707
+            x[e] = __hiloint2double((int)hi, __double2loint(x[e]));
+        }
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e) t[e] = fma(x[e], SVGPFA_EXP_INV_L * 0.03125, MAGIC);   // 64 / ln2

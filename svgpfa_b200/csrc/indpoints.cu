@@ -91,12 +91,15 @@ __global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buf
 // L^-1 in registers and the entries of L read as warp-uniform (broadcast) shared-memory loads.  No block barriers.
 constexpr int KC_WARPS = 4;
 constexpr int KC_LD = 33;                         // odd: lane <-> row accesses are bank-conflict free
-constexpr int KC_WSM = 32 * KC_LD + 32;           // doubles of shared memory per warp: matrix + 1 / L_jj
+constexpr int KC_COL = 64;                        // column broadcast buffer: entries 32..63 stay zero (the rows past the edge)
+constexpr int KC_WSM = 32 * KC_LD + 32 + KC_COL;  // doubles of shared memory per warp: matrix + 1 / L_jj + column buffer
 
-// 8 columns of the factorisation on a window of LEN columns (LEN = 32 - j0)
+// 8 columns of the factorisation on a window of LEN columns (LEN = 32 - j0).  Column j of L reaches the other lanes
+// through a 64-entry shared-memory buffer read with warp-uniform (broadcast) LDS.64: one instruction per entry where a
+// 64-bit shuffle is two, and the shuffles were the kernel's busiest pipe (608 per matrix).
 template <int LEN>
 __device__ __forceinline__ void chol_stage(double (&a)[32], int j0, int lane, int M, double* __restrict__ A,
-                                           double* __restrict__ dinv, bool& bad, double& mydiag) {
+                                           double* __restrict__ dinv, double* __restrict__ colb, bool& bad, double& mydiag) {
 #pragma unroll 1
     for (int j = j0; j < j0 + 8; ++j) {
         const double d = __shfl_sync(0xffffffffu, a[0], j);
@@ -106,11 +109,13 @@ __device__ __forceinline__ void chol_stage(double (&a)[32], int j0, int lane, in
         if (lane == j) mydiag = dg;
         A[lane * KC_LD + j] = lij;
         if (lane == 0) dinv[j] = inv;
+        colb[lane] = lij;
+        __syncwarp();
+        const double* cj = colb + j;
 #pragma unroll
-        for (int kk = 1; kk < LEN; ++kk) {
-            const double lkj = __shfl_sync(0xffffffffu, lij, (j + kk) & 31);
-            a[kk - 1] = fma(-lij, lkj, a[kk]);           // columns past the matrix edge carry garbage, never read
-        }
+        for (int kk = 1; kk < LEN; ++kk)
+            a[kk - 1] = fma(-lij, cj[kk], a[kk]);        // columns past the matrix edge carry garbage, never read
+        __syncwarp();                                    // the buffer is rewritten by the next column
     }
 }
 
@@ -124,6 +129,8 @@ __global__ void __launch_bounds__(32 * KC_WARPS) kzz_chol_warp_kernel(svgpfa_dim
     const int M = ds.M;
     double* A = sm + (size_t)warp * KC_WSM;
     double* dinv = A + 32 * KC_LD;
+    double* colb = dinv + 32;
+    colb[32 + lane] = 0.0;
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
     const double zi = lane < M ? bf.Z[(size_t)dm.R * ds.moff + (size_t)r * M + lane] : 0.0;
     // Kzz (lower triangle) -> A; rows / columns >= M are those of the identity.  Rows t and 30 - t together hold 32
@@ -147,10 +154,10 @@ __global__ void __launch_bounds__(32 * KC_WARPS) kzz_chol_warp_kernel(svgpfa_dim
     __syncwarp();
     bool bad = false;
     double mydiag = 1.0;
-    chol_stage<32>(a, 0, lane, M, A, dinv, bad, mydiag);
-    chol_stage<24>(a, 8, lane, M, A, dinv, bad, mydiag);
-    chol_stage<16>(a, 16, lane, M, A, dinv, bad, mydiag);
-    chol_stage<8>(a, 24, lane, M, A, dinv, bad, mydiag);
+    chol_stage<32>(a, 0, lane, M, A, dinv, colb, bad, mydiag);
+    chol_stage<24>(a, 8, lane, M, A, dinv, colb, bad, mydiag);
+    chol_stage<16>(a, 16, lane, M, A, dinv, colb, bad, mydiag);
+    chol_stage<8>(a, 24, lane, M, A, dinv, colb, bad, mydiag);
     __syncwarp();
     if (bad && lane == 0) {
         if (atomicCAS(bf.info, 0, SVGPFA_INFO_NOT_PD) == 0) { bf.info[1] = r; bf.info[2] = k; }

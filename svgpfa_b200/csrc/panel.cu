@@ -39,45 +39,57 @@ __device__ __forceinline__ double pm_node_time(const svgpfa_dims& dm, int i) {
 
 // ------------------------------------------------------------------------------------------
 // tau[r][n][b P + i] = sum_{s in (r,n), t_s in panel b} l_i(x_s),  l_i(x) = (2/P) sum'_{m<P} T_m(x_i) T_m(x).
-// Warp per segment; lane = (half, i): the two halves take alternate spikes, lane i of a half owns node i of every
-// panel in its half's accumulator row, so the read-modify-writes need no atomics.
+// Warp per segment; lane = (spike slot, node pair): four spikes per iteration, eight lanes per spike, lane p of a spike
+// owns the nodes p and P-1-p.  The first-kind Chebyshev nodes are symmetric, x_{P-1-i} = -x_i, so with E / O the even /
+// odd-degree parts of l_i:  l_i = E + O,  l_{P-1-i} = E - O -- two nodes for one 16-term sum, after the 14-step
+// recurrence for T_m(x) that the eight lanes of a spike share by repeating it (7.5 FP64 instructions per spike and
+// warp against 14 with one node per lane).  Every lane owns its (slot, node) entries of the accumulator rows: the
+// read-modify-writes need no atomics.  Rebuilt per block by the host-buffer entry whenever new spikes arrive.
 // ------------------------------------------------------------------------------------------
 constexpr int PMK_WARPS = 4;
+constexpr int PMK_SLOTS = 4;
 
 __global__ void __launch_bounds__(32 * PMK_WARPS) panel_moments_kernel(svgpfa_dims dm, svgpfa_buffers bf, int n_chunks, int chunk) {
-    extern __shared__ double pm_sm[];                     // [warp][2][NB]
-    const int NB = dm.pm_B * PM_P;
+    extern __shared__ double pm_sm[];                     // [warp][slot][NB + 8]  (+8: the slots' rows fall on different banks)
+    const int NB = dm.pm_B * PM_P, NBP = NB + 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = lane >> 4, i = lane & 15;
-    double* acc = pm_sm + (size_t)warp * 2 * NB;
-    double d[PM_P];                                       // row i of D: (2/P) w_m T_m(x_i), T_m(x_i) = cos(m pi (i + 1/2) / P)
+    const int slot = lane >> 3, i = lane & 7;
+    double* acc = pm_sm + (size_t)warp * PMK_SLOTS * NBP;
+    double de[PM_P / 2], dod[PM_P / 2];                   // row i of D split by parity: (2/P) w_m T_m(x_i), T_m(x_i) = cos(m pi (i + 1/2) / P)
 #pragma unroll
-    for (int m = 0; m < PM_P; ++m) d[m] = (m == 0 ? 1.0 : 2.0) / PM_P * cospi(m * (i + 0.5) / PM_P);
+    for (int m = 0; m < PM_P / 2; ++m) {
+        de[m] = (m == 0 ? 1.0 : 2.0) / PM_P * cospi(2 * m * (i + 0.5) / PM_P);
+        dod[m] = 2.0 / PM_P * cospi((2 * m + 1) * (i + 0.5) / PM_P);
+    }
     const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
     const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
     const double inv_w = 1.0 / dm.pm_w;
     for (int n = nb + warp; n < ne; n += PMK_WARPS) {
         const int64_t s0 = bf.seg_off[(size_t)r * dm.N + n], s1 = bf.seg_off[(size_t)r * dm.N + n + 1];
-        for (int e = lane; e < 2 * NB; e += 32) acc[e] = 0.0;
+        for (int e = lane; e < PMK_SLOTS * NBP; e += 32) acc[e] = 0.0;
         __syncwarp();
-        for (int64_t s = s0 + half; s < s1; s += 2) {
+        for (int64_t s = s0 + slot; s < s1; s += PMK_SLOTS) {
             const double rel = (bf.spike_t[s] - dm.pm_lo) * inv_w;
             int b = (int)floor(rel);
             b = max(0, min(dm.pm_B - 1, b));
-            const double x = fma(2.0, rel - (double)b, -1.0);
-            double tm1 = 1.0, tm = x, li = fma(d[1], x, d[0]);
+            const double x = fma(2.0, rel - (double)b, -1.0), x2 = 2.0 * x;
+            double tm1 = 1.0, tm = x, ev = de[0], od = dod[0] * x;
 #pragma unroll
-            for (int m = 2; m < PM_P; ++m) {
-                const double tn = fma(2.0 * x, tm, -tm1);
-                tm1 = tm;
-                tm = tn;
-                li = fma(d[m], tn, li);
+            for (int m = 1; m < PM_P / 2; ++m) {
+                const double te = fma(x2, tm, -tm1);      // T_{2m}
+                const double to = fma(x2, te, -tm);       // T_{2m+1}
+                ev = fma(de[m], te, ev);
+                od = fma(dod[m], to, od);
+                tm1 = te;
+                tm = to;
             }
-            acc[half * NB + b * PM_P + i] += li;
+            double* row = acc + slot * NBP + b * PM_P;
+            row[i] += ev + od;
+            row[PM_P - 1 - i] += ev - od;
         }
         __syncwarp();
         double* out = bf.pm_tau + ((size_t)r * dm.N + n) * NB;
-        for (int e = lane; e < NB; e += 32) out[e] = acc[e] + acc[NB + e];
+        for (int e = lane; e < NB; e += 32) out[e] = (acc[e] + acc[NBP + e]) + (acc[2 * NBP + e] + acc[3 * NBP + e]);
         __syncwarp();
     }
 }
@@ -391,7 +403,8 @@ extern "C" int svgpfa_panel_moments(const svgpfa_dims* dims, const svgpfa_buffer
     if (n_chunks > (dims->N + PMK_WARPS - 1) / PMK_WARPS) n_chunks = (dims->N + PMK_WARPS - 1) / PMK_WARPS;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
-    const size_t smem = sizeof(double) * PMK_WARPS * 2 * NB;
+    const size_t smem = sizeof(double) * PMK_WARPS * PMK_SLOTS * (NB + 8);
+    SVGPFA_ENSURE_SMEM(smem, panel_moments_kernel);
     panel_moments_kernel<<<(unsigned)(nt * n_chunks), 32 * PMK_WARPS, smem, (cudaStream_t)stream>>>(*dims, *buf, (int)n_chunks, chunk);
     SVGPFA_CHECK_LAUNCH("panel_moments");
     return SVGPFA_OK;
