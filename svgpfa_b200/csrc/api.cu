@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 int svgpfa_launch_spike_gather(const svgpfa_dims* dims, const svgpfa_buffers* buf, bool reuse, cudaStream_t stream);
+bool svgpfa_try_chol_indpoints_fused(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t st);
 
 namespace {
 
@@ -195,9 +196,16 @@ int run_trial_stages(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_
     //  32.41 vs 32.53 ms on the 2000-trial shard -- both kernels are limited by the same FP64 issue port and the spike
     //  kernel alone already holds every register of the SM, so the stages simply run one after the other.)
     if (mark) stage_mark(0, st);
-    if (!(flags & SVGPFA_REUSE_KZZ)) { rc = svgpfa_kzz_chol_fwd(dims, buf, stream); if (rc) return rc; }
+    bool fused = false;
+    if (!(flags & SVGPFA_REUSE_KZZ)) {
+        // M <= 32: Cholesky, inverse and the X / c / alpha / KL stage in one launch (the stage event of kzz_chol then
+        // covers both; indpoints_fwd reads 0)
+        fused = svgpfa_try_chol_indpoints_fused(dims, buf, st);
+        if (fused) { SVGPFA_CHECK_LAUNCH("kzz_chol + indpoints_fwd"); }
+        else { rc = svgpfa_kzz_chol_fwd(dims, buf, stream); if (rc) return rc; }
+    }
     if (mark) stage_mark(1 + SVGPFA_STAGE_KZZ_CHOL, st);
-    rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc;
+    if (!fused) { rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc; }
     if (mark) stage_mark(1 + SVGPFA_STAGE_INDPOINTS_FWD, st);
     rc = svgpfa_quad_latent_fwd(dims, buf, stream); if (rc) return rc;
     if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_FWD, st);

@@ -119,6 +119,12 @@ __device__ __forceinline__ void chol_stage(double (&a)[32], int j0, int lane, in
     }
 }
 
+template <bool LOAD_LI>
+__device__ __forceinline__ void ipfwd_warp_body(const svgpfa_dims& dm, const svgpfa_buffers& bf, int r, int k,
+                                                const svgpfa_latent_desc& ds, double* __restrict__ A, double* __restrict__ vec,
+                                                int lane);
+
+template <bool FUSE_FWD>
 __global__ void __launch_bounds__(32 * KC_WARPS) kzz_chol_warp_kernel(svgpfa_dims dm, svgpfa_buffers bf, int nprob) {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,6 +199,12 @@ __global__ void __launch_bounds__(32 * KC_WARPS) kzz_chol_warp_kernel(svgpfa_dim
         const int i = idx / M, j = idx - i * M;
         Lig[idx] = j <= i ? A[i * KC_LD + j] : 0.0;
     }
+    if (FUSE_FWD) {
+        // X = Li Ls, c, alpha, KL straight from the L^-1 that is still in this warp's tile: saves the launch and the
+        // re-read of Li (3.3 GB at config #5); logdetL is read back by the same lane that wrote it
+        __syncwarp();
+        ipfwd_warp_body<false>(dm, bf, r, k, ds, A, dinv, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -251,19 +263,18 @@ __global__ void __launch_bounds__(IP_THREADS) indpoints_fwd_kernel(svgpfa_dims d
 // (coalesced), lane j owns column j of Ls in registers, X[i][j] = sum_p Li[i][p] Ls[p][j] with the entries of Li read
 // as warp-uniform (broadcast) loads and row i of X written straight from the registers (one coalesced store per row);
 // c = Li m with lane = row, alpha = Li^T c with lane = column.  No block barriers.
-__global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpfa_dims dm, svgpfa_buffers bf, int nprob) {
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int prob = blockIdx.x * KC_WARPS + warp;
-    if (prob >= nprob) return;                        // whole warps leave; there is no block barrier below
-    const int rl = prob / dm.K, k = prob - rl * dm.K, r = dm.r0 + rl;
-    const svgpfa_latent_desc ds = bf.desc[k];
+// A: this warp's [32][KC_LD] tile; LOAD_LI: fetch Li from global memory (otherwise the tile already holds it -- the fused
+// Cholesky kernel below leaves L^-1 there, with unit diagonal in the padding rows, which the zero-padded Ls / m ignore)
+template <bool LOAD_LI>
+__device__ __forceinline__ void ipfwd_warp_body(const svgpfa_dims& dm, const svgpfa_buffers& bf, int r, int k,
+                                                const svgpfa_latent_desc& ds, double* __restrict__ A, double* __restrict__ vec,
+                                                int lane) {
     const int M = ds.M;
-    double* A = sm + (size_t)warp * KC_WSM;           // Li, rows / columns >= M zero
-    double* vec = A + 32 * KC_LD;                     // m, then c
     const size_t mo = (size_t)r * dm.MM + ds.mmoff, vo = (size_t)r * dm.KM + ds.moff;
-    const double* Lig = bf.Li + mo;
-    for (int i = 0; i < 32; ++i) A[i * KC_LD + lane] = (i < M && lane < M) ? Lig[(size_t)i * M + lane] : 0.0;
+    if (LOAD_LI) {
+        const double* Lig = bf.Li + mo;
+        for (int i = 0; i < 32; ++i) A[i * KC_LD + lane] = (i < M && lane < M) ? Lig[(size_t)i * M + lane] : 0.0;
+    }
     vec[lane] = lane < M ? bf.m[(size_t)dm.R * ds.moff + (size_t)r * M + lane] : 0.0;
     const double* cvec = bf.cholvec + (size_t)dm.R * ds.poff + (size_t)r * ds.P;
     double ls[32];                                    // column `lane` of Ls (row-major tril vector, miscUtils.py:135-139)
@@ -304,6 +315,17 @@ __global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpf
     }
     const double tot = warp_sum(part);
     if (lane == 0) bf.kl_rk[(size_t)r * dm.K + k] = 0.5 * (tot + 2.0 * bf.logdetL[(size_t)r * dm.K + k] - (double)M);
+}
+
+__global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpfa_dims dm, svgpfa_buffers bf, int nprob) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prob = blockIdx.x * KC_WARPS + warp;
+    if (prob >= nprob) return;                        // whole warps leave; there is no block barrier below
+    const int rl = prob / dm.K, k = prob - rl * dm.K, r = dm.r0 + rl;
+    const svgpfa_latent_desc ds = bf.desc[k];
+    double* A = sm + (size_t)warp * KC_WSM;           // Li, rows / columns >= M zero
+    ipfwd_warp_body<true>(dm, bf, r, k, ds, A, A + 32 * KC_LD, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -596,13 +618,24 @@ extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers
     if (dims->Mmax <= 32) {
         const int nprob = svgpfa_ntrials(dims) * dims->K;
         const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
-        kzz_chol_warp_kernel<<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
+        kzz_chol_warp_kernel<false><<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
     } else {
         SVGPFA_ENSURE_SMEM(smem, kzz_chol_kernel<false>);
         kzz_chol_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), 64, smem, (cudaStream_t)stream>>>(*dims, *buf);
     }
     SVGPFA_CHECK_LAUNCH("kzz_chol_fwd");
     return SVGPFA_OK;
+}
+
+// svgpfa_kzz_chol_fwd + svgpfa_indpoints_fwd in one launch (M <= 32; the orchestrator uses it whenever both stages run).
+// Returns false when the shape is outside this path.
+bool svgpfa_try_chol_indpoints_fused(const svgpfa_dims* dims, const svgpfa_buffers* buf, cudaStream_t st) {
+    if (dims->Mmax > 32) return false;
+    const int nprob = svgpfa_ntrials(dims) * dims->K;
+    if (nprob == 0) return true;
+    const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
+    kzz_chol_warp_kernel<true><<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, st>>>(*dims, *buf, nprob);
+    return true;
 }
 
 extern "C" int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
