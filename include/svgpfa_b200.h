@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 5
+#define SVGPFA_ABI_VERSION 6
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -294,6 +294,33 @@ enum { SVGPFA_STAGE_KZZ_CHOL = 0, SVGPFA_STAGE_INDPOINTS_FWD, SVGPFA_STAGE_QUAD_
        SVGPFA_STAGE_QUAD_LATENT_BWD, SVGPFA_STAGE_SPIKE, SVGPFA_STAGE_INDPOINTS_BWD, SVGPFA_STAGE_FINALIZE,
        SVGPFA_N_STAGES };
 int svgpfa_set_stage_events(void** events);
+
+/* ---- Vector primitives of the device-resident, shard-aware L-BFGS (svgpfa_b200/lbfgs.py).
+ * The reference optimises every ECM step with torch.optim.LBFGS (stats/svEM.py:218-294: one instance per step, closure
+ * = -eval + backward).  The replacement keeps the optimiser state on the device and runs the two-loop recursion in
+ * coefficient space: an iteration touches the stored (s, y) pairs twice -- svgpfa_lbfgs_multidot (new rows of their
+ * Gram matrix) and svgpfa_lbfgs_combine (the search direction) -- and under trial sharding exchanges one small
+ * all-reduce of those rows.  All vectors are device pointers to n float64, 16-byte aligned unless noted; `ws` is a
+ * device workspace of svgpfa_lbfgs_ws_doubles() float64 (per-block partials, combined in block order: results are
+ * run-to-run reproducible); outputs are device pointers (the caller copies them to the host when it needs to branch).
+ *   multidot : out[i * np + j] = vecs[i] . probes[j],   1 <= nv <= SVGPFA_LBFGS_MAX_VECS, 1 <= np <= 3;
+ *              vecs_host / probes_host are HOST arrays of device pointers
+ *   combine  : d = (accumulate ? d : 0) + sum_i coef_host[i] vecs[i];  out2 = [g . d, max|d|]  (histories longer than
+ *              SVGPFA_LBFGS_MAX_VECS are combined in several calls)
+ *   stats    : out4 = [a . b, max|a|, sum|a|, max|b|]  (b may be NULL)
+ *   update   : s = t d,  y = g - g_prev,  g_prev = g     (torch/optim/lbfgs.py: "do lbfgs update (update memory)")
+ *   step     : x = x0 + t d   (x, x0, d need only 8-byte alignment: x is a slice of a packed parameter buffer) */
+#define SVGPFA_LBFGS_MAX_VECS 64
+#define SVGPFA_LBFGS_MAX_BLOCKS 592
+uint64_t svgpfa_lbfgs_ws_doubles(void);
+int svgpfa_lbfgs_multidot(const double* const* vecs_host, int32_t nv, const double* const* probes_host, int32_t np,
+                          uint64_t n, double* ws, double* out, void* stream);
+int svgpfa_lbfgs_combine(double* d, const double* const* vecs_host, const double* coef_host, int32_t nv,
+                         int32_t accumulate, const double* g, uint64_t n, double* ws, double* out2, void* stream);
+int svgpfa_lbfgs_stats(const double* a, const double* b, uint64_t n, double* ws, double* out4, void* stream);
+int svgpfa_lbfgs_update(double* s, double* y, const double* d, double t, const double* g, double* g_prev,
+                        uint64_t n, void* stream);
+int svgpfa_lbfgs_step(double* x, const double* x0, const double* d, double t, uint64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -83,6 +83,15 @@ SYMBOLS = {
     "svgpfa_elbo_grad_host": (C.c_int, [_P(Dims), _P(Buffers), _P(HostIO), C.c_uint32, C.c_void_p]),
     "svgpfa_set_stage_events": (C.c_int, [C.c_void_p]),
     "svgpfa_release_thread_resources": (C.c_int, []),
+    "svgpfa_lbfgs_ws_doubles": (C.c_uint64, []),
+    "svgpfa_lbfgs_multidot": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "svgpfa_lbfgs_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svgpfa_lbfgs_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svgpfa_lbfgs_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_void_p]),
+    "svgpfa_lbfgs_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_void_p]),
 }
 # include/svgpfa_b200_probes.h (separate library)
 PROBE_SYMBOLS = {

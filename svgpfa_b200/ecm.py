@@ -18,6 +18,15 @@ keeps the reference's step order, optimiser (``torch.optim.LBFGS``, one fresh in
   * a failure on one rank (non-positive-definite Kzz while its Z move) is agreed on at that all-reduce, so all
     ranks leave the step together instead of one of them abandoning the others in a collective.
 
+Two further choices:
+
+  * ``optimizer="b200"`` replaces ``torch.optim.LBFGS`` by ``svgpfa_b200.lbfgs.LBFGS`` (same decisions, state and
+    vector work on the device, coefficient-space two-loop recursion);
+  * ``sharded_steps="joint"`` (needs that optimiser) runs the PER-TRIAL steps as ONE optimisation over the
+    concatenation of all ranks' vectors: every reduction the optimiser decides from is global (one small all-reduce per
+    iteration and per closure call), every closure evaluation is all-reduced by the model, so all ranks stay in
+    lock-step and follow the single-process trajectory -- SURVEY.md §8e option (ii) without gathering gradients.
+
 ``optim_params`` is the reference's hierarchical dictionary (``utils/initUtils.py:13-70``):
 ``em_max_iter``, ``{step}_estimate``, ``{step}_optim_params`` (keyword arguments of ``torch.optim.LBFGS``).
 Works on any object with the model protocol of SURVEY.md §8b; ``process_group=None`` makes it a plain
@@ -60,9 +69,20 @@ def _parameters_and_objective(model, step):
     raise ValueError(f"unknown step {step!r}")
 
 
-def _lbfgs_step(params, objective, lbfgs_kwargs):
+def _optimizer_factory(optimizer):
+    if callable(optimizer):
+        return optimizer
+    if optimizer == "torch":
+        return torch.optim.LBFGS
+    if optimizer == "b200":
+        from .lbfgs import LBFGS
+        return LBFGS
+    raise ValueError(f"optimizer must be 'torch', 'b200' or a factory, not {optimizer!r}")
+
+
+def _lbfgs_step(params, objective, lbfgs_kwargs, factory=torch.optim.LBFGS):
     """One ``optimizer.step(closure)`` on -objective, then one more forward for the value that is logged."""
-    optimizer = torch.optim.LBFGS(params, **lbfgs_kwargs)
+    optimizer = factory(params, **lbfgs_kwargs)
     for p in params:
         p.requires_grad = True
     try:
@@ -87,14 +107,30 @@ def _sum_over_ranks(values, group, device, op=None):
     return t.tolist()
 
 
-def run_step(model, step, lbfgs_kwargs, process_group=None):
+def run_step(model, step, lbfgs_kwargs, process_group=None, optimizer="torch", sharded_steps="blockwise"):
     """Runs one conditional maximisation.  Returns ``(bound, niter, nfeval)``; with a process group the bound of a
-    per-trial step is the sum over ranks and niter / nfeval are the maxima over ranks."""
+    block-wise per-trial step is the sum over ranks and niter / nfeval are the maxima over ranks."""
+    if sharded_steps not in ("blockwise", "joint"):
+        raise ValueError("sharded_steps must be 'blockwise' or 'joint'")
+    factory = _optimizer_factory(optimizer)
     params, objective = _parameters_and_objective(model, step)
+    if process_group is not None and step in SHARDED_STEPS and sharded_steps == "joint":
+        if optimizer == "torch":
+            raise ValueError("sharded_steps='joint' needs the shard-aware optimiser (optimizer='b200')")
+        # one optimisation over all ranks' vectors: global reductions inside the optimiser, every closure evaluation
+        # all-reduced by the model (status included: a failed Cholesky on one rank raises on every rank)
+        previous = getattr(model, "shard_mode", None)
+        model.shard_mode = "reduce"
+        try:
+            bound, niter, nfeval = _lbfgs_step(params, objective, lbfgs_kwargs,
+                                               lambda p, **kw: factory(p, process_group=process_group, **kw))
+        finally:
+            model.shard_mode = previous if previous is not None else "auto"
+        return float(bound.item()), niter, nfeval
     if process_group is None or step not in SHARDED_STEPS:
         saved = [p.detach().clone() for p in params] if step == "mstep_kernels" else None
         try:
-            bound, niter, nfeval = _lbfgs_step(params, objective, lbfgs_kwargs)
+            bound, niter, nfeval = _lbfgs_step(params, objective, lbfgs_kwargs, factory)
         except Exception:
             if saved is not None:                       # a failed kernels step leaves the old hyper-parameters
                 for p, q in zip(params, saved):         # (svEM.py:236,249-253)
@@ -105,7 +141,7 @@ def run_step(model, step, lbfgs_kwargs, process_group=None):
     device = params[0].device
     failed, err, local = 0.0, None, (0.0, 0, 0)
     try:
-        bound, niter, nfeval = _lbfgs_step(params, objective, lbfgs_kwargs)
+        bound, niter, nfeval = _lbfgs_step(params, objective, lbfgs_kwargs, factory)
         if hasattr(model, "checkErrors"):
             model.checkErrors()
         local = (float(bound.item()), niter, nfeval)
@@ -118,7 +154,8 @@ def run_step(model, step, lbfgs_kwargs, process_group=None):
     return total, int(niter), int(nfeval)
 
 
-def maximize(model, optim_params, method="ecm", process_group=None, out=sys.stdout, verbose=True):
+def maximize(model, optim_params, method="ecm", process_group=None, out=sys.stdout, verbose=True, optimizer="torch",
+             sharded_steps="blockwise"):
     """ECM / mECM maximisation of the lower bound.  Returns ``(lower_bound_hist, elapsed_time_hist,
     termination_message, step_log)`` with ``step_log`` rows ``(iteration, step, bound, niter, nfeval)`` -- the
     quantities of the reference's log lines (svEM.py:164-166).  ``process_group`` defaults to the model's."""
@@ -135,7 +172,8 @@ def maximize(model, optim_params, method="ecm", process_group=None, out=sys.stdo
             if not optim_params.get(f"{step}_estimate", True):
                 continue
             try:
-                bound, niter, nfeval = run_step(model, step, optim_params[f"{step}_optim_params"], process_group)
+                bound, niter, nfeval = run_step(model, step, optim_params[f"{step}_optim_params"], process_group,
+                                                optimizer, sharded_steps)
             except Exception as e:                      # every rank gets here together (see run_step)
                 return hist, elapsed, f"Error occured while processing {step} in iteration {it}: {e}", log
             log.append((it, step, bound, niter, nfeval))

@@ -48,7 +48,8 @@ class _ShardedBoundFn(torch.autograd.Function):
         shared = torch.from_numpy(sharding.pack_shared(val.item(), 0.0, 0.0, gnp(full[2 * K], (N, K)),
                                                        gnp(full[2 * K + 1], (N,)), dth))
         model.n_evals += 1
-        if model.pg is not None and sharding.evaluation_is_reduced(flags):
+        if model.pg is not None and (model.shard_mode == "reduce" or
+                                     (model.shard_mode == "auto" and sharding.evaluation_is_reduced(flags))):
             sharding.all_reduce_shared(shared, model.pg)
             model.n_reduced += 1
         lay = sharding.shared_layout(N, K, dth.size)
@@ -78,6 +79,7 @@ class ShardedOracleModel(ecm_driver.OracleModel):
         self.pg, self._pg = pg, pg
         self.K = len(case["kernel_types"])
         self.n_evals = self.n_reduced = 0
+        self.shard_mode = "auto"                 # B200SVLowerBound.shard_mode: "reduce" = every evaluation is a collective
 
     def _leaves(self):
         p = self.p

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--em-iters", type=int, default=2)
     ap.add_argument("--lbfgs-iters", type=int, default=10)
     ap.add_argument("--cpu-trials", type=int, default=8)
+    ap.add_argument("--optimizer", default="torch", choices=("torch", "b200", "both"),
+                    help="torch.optim.LBFGS, the device-resident svgpfa_b200.lbfgs.LBFGS, or one run with each")
     args = ap.parse_args()
     import torch
     import ecm_driver
@@ -46,18 +48,37 @@ def main():
         loss.backward()
         return loss
     opt.step(_closure)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    hist, log = ecm_driver.maximize(model, em_max_iter=args.em_iters, lbfgs_kwargs=kw)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    from svgpfa_b200 import ecm
+    op = {"em_max_iter": args.em_iters}
+    for s in ecm.STEP_ORDER["ecm"]:
+        op[f"{s}_estimate"], op[f"{s}_optim_params"] = True, dict(kw)
+    runs = {}
+    for which in (("torch", "b200") if args.optimizer == "both" else (args.optimizer,)):
+        if runs:                                          # same initial state for the second optimiser
+            model = model_from_case(case, device=dev)
+            float(model.eval())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist, _, _, log = ecm.maximize(model, op, out=None, optimizer=which)
+        torch.cuda.synchronize()
+        runs[which] = (time.perf_counter() - t0, hist, log)
+    first = next(iter(runs))
+    dt, hist, log = runs[first]
     out = {"what": "full svEM (ECM: estep, mstep_embedding, mstep_kernels, mstep_indpointslocs) through the model protocol",
            "config": f"{args.config}: R={cfg['R']} N={cfg['N']} K={cfg['K']} M={cfg['M']} Q={cfg['Q']} mixed={cfg['mixed']}",
-           "em_iters": args.em_iters, "lbfgs_max_iter": args.lbfgs_iters,
+           "em_iters": args.em_iters, "lbfgs_max_iter": args.lbfgs_iters, "optimizer": first,
            "seconds_per_em_iter_gpu": dt / args.em_iters,
            "closure_evals": sum(l[4] for l in log), "bound": [hist[0], hist[-1]],
            "monotone": all(b >= a - 1e-9 * abs(a) for a, b in zip(hist, hist[1:])),
            "steps": [{"iter": l[0], "step": l[1], "bound": l[2], "lbfgs_iters": l[3], "evals": l[4]} for l in log]}
+    if len(runs) > 1:
+        dt2, hist2, log2 = runs["b200"]
+        out["b200_optimizer"] = {"seconds_per_em_iter_gpu": dt2 / args.em_iters, "closure_evals": sum(l[4] for l in log2),
+                                 "bound": [hist2[0], hist2[-1]],
+                                 "same_counts_as_torch": [l[3:] for l in log] == [l[3:] for l in log2],
+                                 "bound_rel_diff_per_step": [abs(a[2] - b[2]) / abs(a[2]) for a, b in zip(log, log2)],
+                                 "steps": [{"iter": l[0], "step": l[1], "bound": l[2], "lbfgs_iters": l[3], "evals": l[4]}
+                                           for l in log2]}
     if args.cpu_trials > 0:
         r_sub = min(args.cpu_trials, cfg["R"])
         sub = synthetic.case_to_numpy(case, 0, r_sub)

@@ -29,6 +29,11 @@ def main():
     ap.add_argument("--max-iter", type=int, default=20)
     ap.add_argument("--out", default=None)
     ap.add_argument("--compare", default=None)
+    ap.add_argument("--optimizer", default="torch", choices=("torch", "b200"),
+                    help="torch.optim.LBFGS or the device-resident svgpfa_b200.lbfgs.LBFGS")
+    ap.add_argument("--sharded-steps", default="blockwise", choices=("blockwise", "joint"),
+                    help="per-trial steps: rank-local optimisations, or one joint optimisation with global reductions "
+                         "(needs --optimizer b200; reproduces the 1-GPU trajectory)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -61,14 +66,16 @@ def main():
             p[f"{s}_optim_params"] = dict(kw)
         return p
 
-    out = {"config": args.config, "world": world, "trial_blocks": [list(b) for b in blocks], "cfg": cfg, "lbfgs": kw}
+    out = {"config": args.config, "world": world, "trial_blocks": [list(b) for b in blocks], "cfg": cfg, "lbfgs": kw,
+           "optimizer": args.optimizer, "sharded_steps": args.sharded_steps}
     for name, estimate in (("shared_steps", ("mstep_embedding", "mstep_kernels")), ("full", ecm.STEP_ORDER["ecm"])):
         case = synthetic.make_case_torch(cfg, dev, seed=0, r0=r0, r1=r1)
         model = model_from_case(case, device=dev, process_group=pg)
         del case
         torch.cuda.synchronize(dev)
         t0 = time.time()
-        hist, elapsed, msg, log = ecm.maximize(model, optim_params(estimate), process_group=pg, out=None)
+        hist, elapsed, msg, log = ecm.maximize(model, optim_params(estimate), process_group=pg, out=None,
+                                               optimizer=args.optimizer, sharded_steps=args.sharded_steps)
         torch.cuda.synchronize(dev)
         out[name] = {"lower_bound_hist": hist, "termination": msg, "wall_s": time.time() - t0,
                      "step_log": [list(row) for row in log],
@@ -88,6 +95,11 @@ def main():
             cmp["full_monotone"] = bool(all(y >= x - 1e-9 * abs(x) for x, y in zip([out["full"]["lower_bound_hist"][0]] + f, f)))
             cmp["full_final_bound_vs_1gpu_rel_diff"] = (out["full"]["lower_bound_hist"][-1] - ref["full"]["lower_bound_hist"][-1]) \
                 / abs(ref["full"]["lower_bound_hist"][-1])
+            if args.sharded_steps == "joint":                 # the per-trial steps follow the 1-GPU trajectory too
+                a, b = out["full"]["step_log"], ref["full"]["step_log"]
+                cmp["full_same_counts"] = [r[:2] + r[3:] for r in a] == [r[:2] + r[3:] for r in b]
+                cmp["full_counts"] = [[r[3:] for r in a], [r[3:] for r in b]]
+                cmp["full_bound_rel_diff"] = [abs(x[2] - y[2]) / abs(y[2]) for x, y in zip(a, b)]
             out["compare_with_" + os.path.basename(args.compare)] = cmp
         text = json.dumps(out)
         print(text)
