@@ -30,7 +30,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
     const int ld = MP + 4;
-    return (size_t)2 * MP * ld + 2 * MP + (size_t)nw * ((bwd ? 2 : 1) * MP * QM_LDT + 3 * 32);
+    (void)bwd;                                    // one tile per warp in both kernels (see quad_latent_mma_kernel)
+    return (size_t)2 * MP * ld + 2 * MP + (size_t)nw * (MP * QM_LDT + 3 * 32);
 }
 
 // Element-wise work (kernel evaluations, their derivatives, row sums) is written as ROLLED loops over a shared
@@ -47,7 +48,7 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 // share in passes of 4 or 3 groups (7 -> 4 + 3, 6 -> 3 + 3): two instantiations of the pass body, no idle warp, at
 // most two padded groups per warp.
 template <int MT, bool BWD>
-__global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 2 : 4)
+__global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 3 : 4)
 quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
     extern __shared__ __align__(16) double sm[];
@@ -65,12 +66,15 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     double* Xs = Lis + MP * LD;                         // [MP][LD]  X; in the adjoint with need_kz: G = X X^T - I
     double* al = Xs + MP * LD;                          // [MP]
     double* zs = al + MP;                               // [MP]
-    constexpr int WSTRIDE = (BWD ? 2 : 1) * MP * LDT + 3 * 32;
+    // ONE [MP][LDT] tile per warp holds, in turn, K, V, W = G V and Li^T W: every product reads the tile into fragment
+    // registers completely before its result is written back (a __syncwarp on either side).  A second tile (round 1:
+    // K / W beside V / Li^T W) cost 9 KB per warp and, with it, the third resident CTA per SM.
+    constexpr int WSTRIDE = MP * LDT + 3 * 32;
     double* wbase = zs + MP + (size_t)warp * WSTRIDE;
-    double* tileV = wbase;                              // [MP][LDT]  (FWD: K, then) V, later Li^T W
-    double* tileU = wbase + (BWD ? MP * LDT : 0);       // [MP][LDT]  K, later W                (BWD only)
-    double* tileK = BWD ? tileU : tileV;
-    double* tt = wbase + (BWD ? 2 : 1) * MP * LDT;      // [32] quadrature nodes of the pass
+    double* tileV = wbase;
+    double* tileU = wbase;
+    double* tileK = wbase;
+    double* tt = wbase + MP * LDT;                      // [32] quadrature nodes of the pass
     double* mbs = tt + 32;                              // [32] mubar
     double* vbs = mbs + 32;                             // [32] varbar
     const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
@@ -297,6 +301,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                 }
             }
         } else {
+            __syncwarp();                                            // every lane is done reading K (abar loop, V product)
 #pragma unroll
             for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
@@ -335,7 +340,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                         for (int qt = 0; qt < NQT; ++qt) dmma(w[it][qt][0], w[it][qt][1], a, b[qt]);
                     }
                 }
-                __syncwarp();                                        // K (tileU) fully consumed by every lane (abar loop)
+                __syncwarp();                                        // V fully consumed by every lane (SYRK, W product)
 #pragma unroll
                 for (int it = 0; it < MT; ++it)
 #pragma unroll
@@ -359,7 +364,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                         for (int qt = 0; qt < NQT; ++qt) dmma(w[jt][qt][0], w[jt][qt][1], a, b[qt]);
                     }
                 }
-                // (the __syncwarp before the W store ordered every lane's V reads -- SYRK and the W product -- before here)
+                __syncwarp();                                        // W fully consumed by every lane
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt)
 #pragma unroll
