@@ -141,7 +141,7 @@ constexpr int PMG_THREADS = 256;
 __host__ __device__ inline int pm_ldc(int KT) { const int kp = 8 * KT; return (kp % 32 == 8 || kp % 32 == 24) ? kp : kp + 8; }
 
 template <int KT, int NCT>
-__global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
+__global__ void __launch_bounds__(PMG_THREADS, 2) panel_weights_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
     extern __shared__ double pg_sm[];                     // C [N4][LDC], rows >= N and columns >= K zero
     constexpr int LDC = (8 * KT % 32 == 8 || 8 * KT % 32 == 24) ? 8 * KT : 8 * KT + 8;
     const int N = dm.N, K = dm.K, NB = dm.pm_B * PM_P, N4 = (N + 3) / 4 * 4;
@@ -152,37 +152,51 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims 
     }
     __syncthreads();
     const int nt = dm.rn ? dm.rn : dm.R;
-    for (int rl = blockIdx.x; rl < nt; rl += gridDim.x) {
+    // Software pipeline over batches of PW k-steps (PW * NCT tau loads per lane): the loads of batch i + 1 -- of the
+    // NEXT trial after a trial's last batch -- are issued before the mma of batch i.  Round-2 history: with the loads
+    // left to the compiler long-scoreboard was the top stall; batched loads (issue all, wait, compute) left the kernel
+    // alternating between a load phase and a compute phase (HBM 43 % + FP64 pipe 46 % of the time, summing to one).
+    constexpr int PW = NCT <= 1 ? 16 : NCT == 2 ? 8 : NCT == 3 ? 5 : NCT == 4 ? 4 : 2;
+    const int nks = N4 / 4, nbe = ((nks + PW - 1) / PW + 1) & ~1;          // batches per trial, padded to an even count
+    double acc[KT][NCT][2];
+    auto load = [&](double (&b)[PW][NCT], int rl, int ks0) {
+        const double* tau = bf.pm_tau + (size_t)(dm.r0 + rl) * N * NB + 8 * NCT * warp + g;
+#pragma unroll
+        for (int u = 0; u < PW; ++u) {
+            const int n = 4 * (ks0 + u) + tg;
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) b[u][c] = n < N ? __ldg(tau + (size_t)n * NB + 8 * c) : 0.0;
+        }
+    };
+    auto compute = [&](const double (&b)[PW][NCT], int ks0) {
+#pragma unroll
+        for (int u = 0; u < PW; ++u) {
+            const int n = 4 * (ks0 + u) + tg;
+            if (4 * (ks0 + u) >= N4) break;                // warp-uniform
+            double a[KT];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) a[kt] = pg_sm[n * LDC + 8 * kt + g];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int c = 0; c < NCT; ++c) pm_dmma(acc[kt][c][0], acc[kt][c][1], a[kt], b[u][c]);
+        }
+    };
+    double b0[PW][NCT], b1[PW][NCT];
+    int rl = blockIdx.x;
+    if (rl < nt) load(b0, rl, 0);
+    for (; rl < nt; rl += gridDim.x) {
         const int r = dm.r0 + rl;
-        const double* tau = bf.pm_tau + (size_t)r * N * NB + 8 * NCT * warp + g;
-        double acc[KT][NCT][2];
 #pragma unroll
         for (int a = 0; a < KT; ++a)
 #pragma unroll
             for (int c = 0; c < NCT; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
-        // batches of PW k-steps: all tau loads of a batch are issued before its first mma (ncu: long-scoreboard was the top
-        // stall with the loads left to the compiler's scheduling)
-        constexpr int PW = 8;
-        for (int ks0 = 0; ks0 < N4 / 4; ks0 += PW) {
-            double b[PW][NCT];
-#pragma unroll
-            for (int u = 0; u < PW; ++u) {
-                const int n = 4 * (ks0 + u) + tg;
-#pragma unroll
-                for (int c = 0; c < NCT; ++c) b[u][c] = n < N ? __ldg(tau + (size_t)n * NB + 8 * c) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < PW; ++u) {
-                const int n = 4 * (ks0 + u) + tg;
-                if (4 * (ks0 + u) >= N4) break;            // warp-uniform
-                double a[KT];
-#pragma unroll
-                for (int kt = 0; kt < KT; ++kt) a[kt] = pg_sm[n * LDC + 8 * kt + g];
-#pragma unroll
-                for (int kt = 0; kt < KT; ++kt)
-#pragma unroll
-                    for (int c = 0; c < NCT; ++c) pm_dmma(acc[kt][c][0], acc[kt][c][1], a[kt], b[u][c]);
-            }
+        for (int bi = 0; bi < nbe; bi += 2) {
+            load(b1, rl, (bi + 1) * PW);
+            compute(b0, bi * PW);
+            if (bi + 2 < nbe) load(b0, rl, (bi + 2) * PW);
+            else if (rl + (int)gridDim.x < nt) load(b0, rl + gridDim.x, 0);
+            compute(b1, (bi + 1) * PW);
         }
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
@@ -207,7 +221,7 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_weights_kernel(svgpfa_dims 
 constexpr int PMD_ROWS = 256;
 
 template <int KT>
-__global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, svgpfa_buffers bf, double* __restrict__ gC) {
+__global__ void __launch_bounds__(PMG_THREADS, 2) panel_dC_kernel(svgpfa_dims dm, svgpfa_buffers bf, double* __restrict__ gC) {
     extern __shared__ double pd_sm[];                     // mun of one trial, [8 KT][NB + 4], rows >= K zero
     const int N = dm.N, K = dm.K, NB = dm.pm_B * PM_P, LDM = NB + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tg = lane & 3;
@@ -219,7 +233,37 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, s
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) acc[t][kt][0] = acc[t][kt][1] = 0.0;
     for (int idx = tid; idx < 8 * KT * LDM; idx += PMG_THREADS) pd_sm[idx] = 0.0;      // padding rows / columns stay zero
-    for (int rl = blockIdx.y; rl < nt; rl += gridDim.y) {
+    // Software pipeline over batches of PW k-steps (= 64 nodes of one 8-row tile; a trial is 4 NB / 64 batches, an even
+    // count): the tau loads of the next batch -- of the NEXT trial after a trial's last batch, ahead of the barrier that
+    // swaps mun -- are issued before the mma of the current one (see panel_weights_kernel).
+    constexpr int PW = 16;
+    const int bpt = NB / 64, nbatch = 4 * bpt;            // batches per row tile, per trial
+    auto load = [&](double (&a)[PW], int rl, int j) {
+        const int t = j / bpt, ks0 = (j - t * bpt) * PW;
+        const int n = row0 + 8 * t + g;
+        if (row0 + 8 * t >= N) return;                    // warp-uniform: rows past the matrix, never computed on
+        const double* tau = bf.pm_tau + ((size_t)(dm.r0 + rl) * N + (n < N ? n : N - 1)) * NB + tg + 4 * ks0;
+#pragma unroll
+        for (int u = 0; u < PW; ++u) a[u] = n < N ? __ldg(tau + 4 * u) : 0.0;
+    };
+    auto compute = [&](const double (&a)[PW], int j) {
+        const int t = j / bpt, ks0 = (j - t * bpt) * PW;
+        if (row0 + 8 * t >= N) return;
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {                  // static accumulator index
+            if (tt == t) {
+#pragma unroll
+                for (int u = 0; u < PW; ++u)
+#pragma unroll
+                    for (int kt = 0; kt < KT; ++kt)
+                        pm_dmma(acc[tt][kt][0], acc[tt][kt][1], a[u], pd_sm[(8 * kt + g) * LDM + 4 * (ks0 + u) + tg]);
+            }
+        }
+    };
+    double a0[PW], a1[PW];
+    int rl = blockIdx.y;
+    if (rl < nt) load(a0, rl, 0);
+    for (; rl < nt; rl += gridDim.y) {
         const int r = dm.r0 + rl;
         __syncthreads();                                  // the previous trial's mun has been consumed
         for (int idx = tid; idx < K * NB; idx += PMG_THREADS) {
@@ -227,22 +271,12 @@ __global__ void __launch_bounds__(PMG_THREADS) panel_dC_kernel(svgpfa_dims dm, s
             pd_sm[kk * LDM + i] = bf.pm_mun[((size_t)r * K + kk) * NB + i];
         }
         __syncthreads();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int n = row0 + 8 * t + g;
-            if (row0 + 8 * t >= N) break;                 // warp-uniform
-            const double* tau = bf.pm_tau + ((size_t)r * N + (n < N ? n : N - 1)) * NB + tg;
-            constexpr int PW = 16;                         // tau loads in flight per lane (ncu: long-scoreboard 25 per issue)
-            for (int ks0 = 0; ks0 < NB / 4; ks0 += PW) {   // NB / 4 is a multiple of 16
-                double a[PW];
-#pragma unroll
-                for (int u = 0; u < PW; ++u) a[u] = n < N ? __ldg(tau + 4 * (ks0 + u)) : 0.0;
-#pragma unroll
-                for (int u = 0; u < PW; ++u)
-#pragma unroll
-                    for (int kt = 0; kt < KT; ++kt)
-                        pm_dmma(acc[t][kt][0], acc[t][kt][1], a[u], pd_sm[(8 * kt + g) * LDM + 4 * (ks0 + u) + tg]);
-            }
+        for (int j = 0; j < nbatch; j += 2) {
+            load(a1, rl, j + 1);
+            compute(a0, j);
+            if (j + 2 < nbatch) load(a0, rl, j + 2);
+            else if (rl + (int)gridDim.y < nt) load(a0, rl + gridDim.y, 0);
+            compute(a1, j + 1);
         }
     }
 #pragma unroll
