@@ -135,6 +135,22 @@ class _LazySpikeMeans:
         return iter(self._materialise())
 
 
+class _LazySpikeVars(_LazySpikeMeans):
+    """Per-trial (S_r, K) latent variances at the spike times, computed on first access.  The exponential link never
+    reads them (expectedLogLikelihood.py:210-213), so the lower-bound path does not compute them; a caller that does
+    (PointProcessELLQuad, expectedLogLikelihood.py:215-255, or a diagnostic) gets the values of
+    SVPosteriorOnLatentsAssocTimes.computeMeansAndVars (svPosteriorOnLatents.py:265-300) from the quadrature kernels
+    run at the spike times."""
+
+    def _materialise(self):
+        if self._rows is None:
+            if self._model._param_snapshot(with_cov=True) != self._snapshot:
+                raise RuntimeError("the spike-time variances of these statistics were not materialised before the "
+                                   "model's parameters changed")
+            self._rows = self._model._spike_time_vars(self._off)
+        return self._rows
+
+
 class B200SVLowerBound:
     _PENDING_SLOTS = 8
     _stats_serial = 0
@@ -667,9 +683,45 @@ class B200SVLowerBound:
             _cabi.check(_cabi.lib().svgpfa_spike_latent_means(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
         return mu_s[:self._S * self._K].view(self._S, self._K)
 
+    def _spike_time_vars(self, off, budget_bytes=1 << 30):
+        """[(S_r, K) variances at the spike times of trial r]: svgpfa_quad_latent_fwd over blocks of trials with the
+        (padded) spike times of a trial in place of its quadrature nodes."""
+        dev = self._dev()
+        R, K = self._R, self._K
+        counts = [off[r + 1] - off[r] for r in range(R)]
+        rows = [None] * R
+        spikes = self._spike_t.to(_F64) if self._spike_t.dtype != _F64 else self._spike_t
+        lib = _cabi.lib()
+        r0 = 0
+        while r0 < R:
+            T, r1 = max(counts[r0], 1), r0 + 1
+            while r1 < R and max(T, counts[r1]) * (r1 + 1 - r0) * K * 16 <= budget_bytes:
+                T = max(T, counts[r1])
+                r1 += 1
+            n = r1 - r0
+            t = torch.zeros(n, T, dtype=_F64, device=dev)
+            for i in range(n):
+                if counts[r0 + i]:
+                    t[i, :counts[r0 + i]] = spikes[off[r0 + i]:off[r0 + i + 1]]
+            mu = torch.empty(n * T * K, dtype=_F64, device=dev)
+            var = torch.empty(n * T * K, dtype=_F64, device=dev)
+            dims = _cabi.Dims.from_buffer_copy(self._dims)
+            dims.Q, dims.r0, dims.rn = T, r0, n
+            b = _cabi.Buffers.from_buffer_copy(self._bufs)
+            # the kernels index these arrays by the GLOBAL trial number: bias the pointers by the block's first trial
+            b.tq = t.data_ptr() - 8 * r0 * T
+            b.mu_q, b.var_q = mu.data_ptr() - 8 * r0 * T * K, var.data_ptr() - 8 * r0 * T * K
+            with torch.cuda.device(dev):
+                _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(dims), ctypes.byref(b), self._stream()))
+            var = var.view(n, T, K)
+            for i in range(n):
+                rows[r0 + i] = var[i, :counts[r0 + i]]
+            r0 = r1
+        return rows
+
     def computeSVPosteriorOnLatentsStats(self):
-        """Latent posterior statistics at quadrature points (mean, var: (R,Q,K)) and at spike times
-        (mean only: the exponential link never reads the variance).  Layout follows
+        """Latent posterior statistics at quadrature points (mean, var: (R,Q,K)) and at spike times (means; the
+        variances, which the exponential link never reads, are a lazy sequence computed on first access).  Layout follows
         expectedLogLikelihood.py:141-147; the per-trial spike tensors are views of one (S,K) buffer.
 
         With cached statistics the spike part of the expected log-likelihood is linear in C with coefficients
@@ -703,15 +755,18 @@ class B200SVLowerBound:
         if panel:
             stats["_b200_gsum"] = self._ws["gsum"].clone()
             self._gsum_key = (serial, None)
-            stats["assocTimes"] = (_LazySpikeMeans(self, off, self._param_snapshot()), [None] * R)
+            stats["assocTimes"] = (_LazySpikeMeans(self, off, self._param_snapshot()),
+                                   _LazySpikeVars(self, off, self._param_snapshot(with_cov=True)))
         else:
             mu_s = self._spike_time_means()
             stats["_b200_mu_s"] = mu_s
-            stats["assocTimes"] = ([mu_s[off[r]:off[r + 1]] for r in range(R)], [None] * R)
+            stats["assocTimes"] = ([mu_s[off[r]:off[r + 1]] for r in range(R)],
+                                   _LazySpikeVars(self, off, self._param_snapshot(with_cov=True)))
         return stats
 
-    def _param_snapshot(self):
-        return (self._Zbuf._version, self._thbuf._version, self._mbuf._version, self._reg)
+    def _param_snapshot(self, with_cov=False):
+        snap = (self._Zbuf._version, self._thbuf._version, self._mbuf._version, self._reg)
+        return snap + (self._cvbuf._version,) if with_cov else snap
 
     def evalELLSumAcrossTrialsAndNeurons(self, svPosteriorOnLatentsStats=None):
         """Expected log-likelihood only (no KL).  With cached statistics it is a function of (C, d)

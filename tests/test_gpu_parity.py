@@ -152,6 +152,10 @@ def test_cached_stats_path():
         assert rel_err(stats["allTimes"][1].cpu().numpy(), ref["quad_latent_var"]) <= 1e-9
         mu_s = torch.cat(list(stats["assocTimes"][0]), 0).cpu().numpy()
         assert rel_err(mu_s, ref["spike_latent_mean"]) <= 1e-9
+        # the variances at the spike times (never read by the exponential link: computed on first access)
+        var_s = torch.cat(list(stats["assocTimes"][1]), 0).cpu().numpy()
+        assert var_s.shape == ref["spike_latent_var"].shape
+        assert rel_err(var_s, ref["spike_latent_var"]) <= 1e-9
         set_requires_grad(model, posterior=False, embedding=True, kernels=False, indlocs=False)
         v = model.evalELLSumAcrossTrialsAndNeurons(svPosteriorOnLatentsStats=stats)
         (-v).backward()
