@@ -38,59 +38,112 @@ __device__ __forceinline__ double pm_node_time(const svgpfa_dims& dm, int i) {
 }
 
 // ------------------------------------------------------------------------------------------
-// tau[r][n][b P + i] = sum_{s in (r,n), t_s in panel b} l_i(x_s),  l_i(x) = (2/P) sum'_{m<P} T_m(x_i) T_m(x).
-// Warp per segment; lane = (spike slot, node pair): four spikes per iteration, eight lanes per spike, lane p of a spike
-// owns the nodes p and P-1-p.  The first-kind Chebyshev nodes are symmetric, x_{P-1-i} = -x_i, so with E / O the even /
-// odd-degree parts of l_i:  l_i = E + O,  l_{P-1-i} = E - O -- two nodes for one 16-term sum, after the 14-step
-// recurrence for T_m(x) that the eight lanes of a spike share by repeating it (7.5 FP64 instructions per spike and
-// warp against 14 with one node per lane).  Every lane owns its (slot, node) entries of the accumulator rows: the
-// read-modify-writes need no atomics.  Rebuilt per block by the host-buffer entry whenever new spikes arrive.
+// tau[r][n][b P + i] = sum_{s in (r,n), t_s in panel b} l_i(x_s),  l_i(x) = sum_m D[i][m] T_m(x),
+// D[i][m] = (2/P) w_m T_m(x_i)  (w_0 = 1/2; first-kind Chebyshev nodes x_i).
+// Warp per (trial, neuron) segment, in two steps on the FP64 tensor path:
+//   1. Chebyshev moments of the segment's panels,  c[m][b] = sum_{s in panel b} T_m(x_s):  lane <-> spike (32 per
+//      iteration, one 14-step recurrence each, no repetition), the T values go through a shared-memory tile into
+//      A fragments and are summed per panel by mma against the INDICATOR matrix  Ind[s][b] = (panel(s) == b)  --
+//      a segmented reduction with exact FP64 accumulation and no atomics / read-modify-writes;
+//   2. tau = D c, a 16 x 16 by 16 x B product per segment (8 mma per 8 panels), written straight from the fragments.
+// Round-2 history: the first version gave 8 lanes to a spike, each repeating the recurrence and summing 16 terms for its
+// node pair into shared-memory accumulators (13 ms per 20 000 trials of config #5: 240 FP64 lane-operations per spike and
+// a zero / read-modify-write / reduce cycle of the accumulator rows per segment).  Rebuilt per block by the
+// host-buffer entry whenever new spikes arrive.
 // ------------------------------------------------------------------------------------------
 constexpr int PMK_WARPS = 4;
-constexpr int PMK_SLOTS = 4;
+constexpr int PMK_LDT = 20;                              // leading dimension of the [spike][degree] tile (conflict-free fragments)
 
+template <int NT>                                         // NT = ceil(panels / 8) column tiles
 __global__ void __launch_bounds__(32 * PMK_WARPS) panel_moments_kernel(svgpfa_dims dm, svgpfa_buffers bf, int n_chunks, int chunk) {
-    extern __shared__ double pm_sm[];                     // [warp][slot][NB + 8]  (+8: the slots' rows fall on different banks)
-    const int NB = dm.pm_B * PM_P, NBP = NB + 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = lane >> 3, i = lane & 7;
-    double* acc = pm_sm + (size_t)warp * PMK_SLOTS * NBP;
-    double de[PM_P / 2], dod[PM_P / 2];                   // row i of D split by parity: (2/P) w_m T_m(x_i), T_m(x_i) = cos(m pi (i + 1/2) / P)
+    constexpr int LDC = 8 * NT + 4;
+    __shared__ double Ts_all[PMK_WARPS][32 * PMK_LDT];
+    __shared__ double Cs_all[PMK_WARPS][PM_P * LDC];
+    const int NB = dm.pm_B * PM_P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+    double* Ts = Ts_all[warp];
+    double* Cs = Cs_all[warp];
+    double dfrag[2][4];                                   // A fragments of D: D[8 it + g][4 ks + tg]
 #pragma unroll
-    for (int m = 0; m < PM_P / 2; ++m) {
-        de[m] = (m == 0 ? 1.0 : 2.0) / PM_P * cospi(2 * m * (i + 0.5) / PM_P);
-        dod[m] = 2.0 / PM_P * cospi((2 * m + 1) * (i + 0.5) / PM_P);
-    }
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int i = 8 * it + g, m = 4 * ks + tg;
+            dfrag[it][ks] = (m == 0 ? 1.0 : 2.0) / PM_P * cospi(m * (i + 0.5) / PM_P);
+        }
     const int rl = blockIdx.x / n_chunks, r = dm.r0 + rl, nc = blockIdx.x - rl * n_chunks;
     const int nb = nc * chunk, ne = min(dm.N, nb + chunk);
     const double inv_w = 1.0 / dm.pm_w;
     for (int n = nb + warp; n < ne; n += PMK_WARPS) {
         const int64_t s0 = bf.seg_off[(size_t)r * dm.N + n], s1 = bf.seg_off[(size_t)r * dm.N + n + 1];
-        for (int e = lane; e < PMK_SLOTS * NBP; e += 32) acc[e] = 0.0;
-        __syncwarp();
-        for (int64_t s = s0 + slot; s < s1; s += PMK_SLOTS) {
-            const double rel = (bf.spike_t[s] - dm.pm_lo) * inv_w;
-            int b = (int)floor(rel);
-            b = max(0, min(dm.pm_B - 1, b));
-            const double x = fma(2.0, rel - (double)b, -1.0), x2 = 2.0 * x;
-            double tm1 = 1.0, tm = x, ev = de[0], od = dod[0] * x;
-#pragma unroll
-            for (int m = 1; m < PM_P / 2; ++m) {
-                const double te = fma(x2, tm, -tm1);      // T_{2m}
-                const double to = fma(x2, te, -tm);       // T_{2m+1}
-                ev = fma(de[m], te, ev);
-                od = fma(dod[m], to, od);
-                tm1 = te;
-                tm = to;
-            }
-            double* row = acc + slot * NBP + b * PM_P;
-            row[i] += ev + od;
-            row[PM_P - 1 - i] += ev - od;
-        }
-        __syncwarp();
         double* out = bf.pm_tau + ((size_t)r * dm.N + n) * NB;
-        for (int e = lane; e < NB; e += 32) out[e] = (acc[e] + acc[NBP + e]) + (acc[2 * NBP + e] + acc[3 * NBP + e]);
+        if (s1 <= s0) {                                   // no spikes: a row of zeros
+            for (int e = lane; e < NB; e += 32) out[e] = 0.0;
+            continue;
+        }
+        double c[2][NT][2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) c[it][nt][0] = c[it][nt][1] = 0.0;
+        for (int64_t base = s0; base < s1; base += 32) {
+            const int64_t s = base + lane;
+            int pb = -1;                                  // panel of this lane's spike; -1: no spike (matches no column)
+            double t[PM_P];
+            if (s < s1) {
+                const double rel = (bf.spike_t[s] - dm.pm_lo) * inv_w;
+                pb = max(0, min(dm.pm_B - 1, (int)floor(rel)));
+                const double x = fma(2.0, rel - (double)pb, -1.0), x2 = 2.0 * x;
+                t[0] = 1.0;
+                t[1] = x;
+#pragma unroll
+                for (int m = 2; m < PM_P; ++m) t[m] = fma(x2, t[m - 1], -t[m - 2]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < PM_P; ++m) t[m] = 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < PM_P; m += 2) *reinterpret_cast<double2*>(Ts + lane * PMK_LDT + m) = make_double2(t[m], t[m + 1]);
+            __syncwarp();
+            const int nk = (int)min((int64_t)8, (s1 - base + 3) / 4);       // k-steps of 4 spikes
+            for (int j = 0; j < nk; ++j) {
+                const double a0 = Ts[(4 * j + tg) * PMK_LDT + g], a1 = Ts[(4 * j + tg) * PMK_LDT + g + 8];
+                const int bs = __shfl_sync(0xffffffffu, pb, 4 * j + tg);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double ind = (bs == 8 * nt + g) ? 1.0 : 0.0;      // B[k = spike tg][n = panel g]
+                    pm_dmma(c[0][nt][0], c[0][nt][1], a0, ind);
+                    pm_dmma(c[1][nt][0], c[1][nt][1], a1, ind);
+                }
+            }
+            __syncwarp();                                 // the tile is rewritten by the next 32 spikes
+        }
+        // tau = D c: c from accumulator layout to B-fragment layout through shared memory
+#pragma unroll
+        for (int it = 0; it < 2; ++it)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                *reinterpret_cast<double2*>(Cs + (8 * it + g) * LDC + 8 * nt + 2 * tg) = make_double2(c[it][nt][0], c[it][nt][1]);
         __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            double ta[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const double bv = Cs[(4 * ks + tg) * LDC + 8 * nt + g];
+                pm_dmma(ta[0][0], ta[0][1], dfrag[0][ks], bv);
+                pm_dmma(ta[1][0], ta[1][1], dfrag[1][ks], bv);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int pbn = 8 * nt + 2 * tg + e;      // panel; node 8 it + g
+                if (pbn < dm.pm_B) {
+                    out[pbn * PM_P + g] = ta[0][e];
+                    out[pbn * PM_P + 8 + g] = ta[1][e];
+                }
+            }
+        }
+        __syncwarp();                                     // Cs is rewritten by the next segment
     }
 }
 
@@ -431,15 +484,19 @@ extern "C" int svgpfa_panel_moments(const svgpfa_dims* dims, const svgpfa_buffer
     if (!panel_args_ok(dims, buf)) return svgpfa_set_error(SVGPFA_E_ARG, "panel_moments", cudaSuccess);
     const int nt = svgpfa_ntrials(dims);
     if (nt == 0 || dims->N == 0) return SVGPFA_OK;
-    const int NB = dims->pm_B * PM_P;
     long n_chunks = ((long)svgpfa_sm_count() * 16 + nt - 1) / nt;      // enough CTAs to fill the machine when R is small
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > (dims->N + PMK_WARPS - 1) / PMK_WARPS) n_chunks = (dims->N + PMK_WARPS - 1) / PMK_WARPS;
     const int chunk = (int)((dims->N + n_chunks - 1) / n_chunks);
     n_chunks = (dims->N + chunk - 1) / chunk;
-    const size_t smem = sizeof(double) * PMK_WARPS * PMK_SLOTS * (NB + 8);
-    SVGPFA_ENSURE_SMEM(smem, panel_moments_kernel);
-    panel_moments_kernel<<<(unsigned)(nt * n_chunks), 32 * PMK_WARPS, smem, (cudaStream_t)stream>>>(*dims, *buf, (int)n_chunks, chunk);
+    const unsigned grid = (unsigned)(nt * n_chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((dims->pm_B + 7) / 8) {
+        case 1: panel_moments_kernel<1><<<grid, 32 * PMK_WARPS, 0, st>>>(*dims, *buf, (int)n_chunks, chunk); break;
+        case 2: panel_moments_kernel<2><<<grid, 32 * PMK_WARPS, 0, st>>>(*dims, *buf, (int)n_chunks, chunk); break;
+        case 3: panel_moments_kernel<3><<<grid, 32 * PMK_WARPS, 0, st>>>(*dims, *buf, (int)n_chunks, chunk); break;
+        default: panel_moments_kernel<4><<<grid, 32 * PMK_WARPS, 0, st>>>(*dims, *buf, (int)n_chunks, chunk); break;
+    }
     SVGPFA_CHECK_LAUNCH("panel_moments");
     return SVGPFA_OK;
 }
