@@ -11,10 +11,11 @@ Q=200; it fits one B200).  With N GPUs the same R trials are sharded over the ra
 and the packed [ELBO | dC | dd | dtheta] buffer is all-reduced once per evaluation.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (spike_fwd_bwd): FP64-pipe bound.  achieved = (F_spike + N_exp * c_exp)/t with
-                F_spike, N_exp from SURVEY.md §8d, c_exp = measured DFMA-flops-per-libdevice-exp, t = the
-                kernel's mean device time inside the timed region (CUDA events recorded by the library);
-                peak = DFMA throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry).
+  roofline      the stage that takes the most time (round 2: quad_latent_bwd), FP64-pipe bound.  achieved = (SURVEY.md
+                8d's algorithmic flops of the stage + 26 flop-equivalents per kernel evaluation / exp) / t, t = the
+                stage's mean device time inside the timed region (CUDA events recorded by the library on its stream);
+                peak = DFMA throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry); roofline.stages
+                carries the same figures for every stage, roofline.spike_term the algorithm of the spike-time term
   stages_ms     mean device time of every kernel stage inside the timed region
   cpu_baseline  the oracle port timed on this box's host cores on a bounded sample of the same workload, with the
                 parity of EVERY gradient group of the timed configuration on that sample

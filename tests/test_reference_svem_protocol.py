@@ -53,3 +53,37 @@ def test_unmodified_svem_and_ecm_driver_issue_the_same_calls():
         assert (it, name, niter, nfeval) == (int(row[0]), row[1], int(row[3]), int(row[4]))
         assert f"{bound:f}" == row[2]                      # same deterministic CPU arithmetic: same printed bound
     assert hist == hist_ref                                # bit-identical lower-bound history
+
+
+def test_unmodified_svem_runs_on_the_b200_optimiser_through_the_patch():
+    """``svgpfa_b200.lbfgs.patched_torch_lbfgs`` swaps the device-resident optimiser in underneath the UNMODIFIED
+    ``SVEM_PyTorch`` (which builds ``torch.optim.LBFGS`` by name, svEM.py:221,229,243,262): same step log as the
+    unpatched run -- niter, nfeval of all 8 steps, printed bounds to 1e-9.  (CPU: the torch implementation of the vector
+    primitives is bound in; on a GPU the default is the CUDA library.)"""
+    sys.path.insert(0, os.path.dirname(__file__))
+    import ecm_driver
+    from vector_ops_torch import TorchVectorOps
+    from svgpfa_b200.lbfgs import LBFGS, patched_torch_lbfgs
+    ref_harness.import_reference()
+    import svGPFA.stats.svEM as ref_svem
+    case, _ = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed.npz"))
+    torch.set_num_threads(1)
+    pat = re.compile(r"Iteration (\d+), (\w+) end: ([-\d.eE+naif]+), niter: (\d+), nfeval: (\d+)")
+
+    def run():
+        out = io.StringIO()
+        hist, _, term, _ = ref_svem.SVEM_PyTorch().maximize(
+            model=ecm_driver.OracleModel(case), optim_params=_optim_params(2), method="ecm", out=out)
+        assert "Maximum number of iterations" in term.message
+        return hist, [pat.match(line).groups() for line in out.getvalue().splitlines() if pat.match(line)]
+    original = torch.optim.LBFGS
+    hist_a, rows_a = run()
+    with patched_torch_lbfgs(ops=TorchVectorOps()):
+        assert issubclass(torch.optim.LBFGS, LBFGS)
+        hist_b, rows_b = run()
+    assert torch.optim.LBFGS is original
+    assert len(rows_a) == len(rows_b) == 8
+    for a, b in zip(rows_a, rows_b):
+        assert (a[0], a[1], a[3], a[4]) == (b[0], b[1], b[3], b[4])
+        assert float(b[2]) == pytest.approx(float(a[2]), rel=1e-9)
+    assert hist_b == pytest.approx(hist_a, rel=1e-9)
