@@ -98,21 +98,25 @@ __global__ void __launch_bounds__(LB_THREADS) lb_multidot_kernel(LbPtrs vp, LbPt
     }
 }
 
-// out[o] = sum (or max, bit o of max_mask) over the nb block partials of output o, in block order
-__global__ void lb_reduce_kernel(const double* __restrict__ part, int nb, int nout, uint64_t max_mask, double* __restrict__ out) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+// out[o] = sum (or max, bit o of max_mask) over the nb block partials of output o: one warp per output, lane-strided
+// loads (one round of memory latency; a thread per output walking 592 partials took 30-50 us) and a butterfly in a
+// fixed order, so the result does not depend on the launch
+constexpr int LB_RED_WARPS = 4;
+__global__ void __launch_bounds__(32 * LB_RED_WARPS) lb_reduce_kernel(const double* __restrict__ part, int nb, int nout, uint64_t max_mask,
+                                                                     double* __restrict__ out) {
+    const int o = blockIdx.x * LB_RED_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= nout) return;
     const double* p = part + (size_t)o * nb;
     if ((max_mask >> (o & 63)) & 1) {
         double m = 0.0;
-        for (int b = 0; b < nb; ++b) m = fmax(m, p[b]);
-        out[o] = m;
+        for (int b = lane; b < nb; b += 32) m = fmax(m, p[b]);
+        m = warp_max(m);
+        if (lane == 0) out[o] = m;
     } else {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int b = 0;
-        for (; b + 3 < nb; b += 4) { s0 += p[b]; s1 += p[b + 1]; s2 += p[b + 2]; s3 += p[b + 3]; }
-        for (; b < nb; ++b) s0 += p[b];
-        out[o] = (s0 + s1) + (s2 + s3);
+        double s = 0.0;
+        for (int b = lane; b < nb; b += 32) s += p[b];
+        s = warp_sum(s);
+        if (lane == 0) out[o] = s;
     }
 }
 
@@ -266,7 +270,7 @@ extern "C" int svgpfa_lbfgs_multidot(const double* const* vecs_host, int32_t nv,
     else if (np == 2) lb_multidot_kernel<2><<<grid, LB_THREADS, 0, st>>>(vp, pp, n, ws);
     else lb_multidot_kernel<3><<<grid, LB_THREADS, 0, st>>>(vp, pp, n, ws);
     const int nout = nv * np;
-    lb_reduce_kernel<<<(nout + 63) / 64, 64, 0, st>>>(ws, nb, nout, 0ull, out);
+    lb_reduce_kernel<<<(nout + LB_RED_WARPS - 1) / LB_RED_WARPS, 32 * LB_RED_WARPS, 0, st>>>(ws, nb, nout, 0ull, out);
     SVGPFA_CHECK_LAUNCH("lbfgs_multidot");
     return SVGPFA_OK;
 }
@@ -286,7 +290,7 @@ extern "C" int svgpfa_lbfgs_combine(double* d, const double* const* vecs_host, c
     const int nb = lb_blocks(n, 4);
     if (accumulate) lb_combine_kernel<true><<<nb, LB_THREADS, 0, st>>>(vp, cf, nv, d, g, n, ws);
     else lb_combine_kernel<false><<<nb, LB_THREADS, 0, st>>>(vp, cf, nv, d, g, n, ws);
-    lb_reduce_kernel<<<1, 64, 0, st>>>(ws, nb, 2, 2ull, out2);
+    lb_reduce_kernel<<<1, 32 * LB_RED_WARPS, 0, st>>>(ws, nb, 2, 2ull, out2);
     SVGPFA_CHECK_LAUNCH("lbfgs_combine");
     return SVGPFA_OK;
 }
@@ -297,7 +301,7 @@ extern "C" int svgpfa_lbfgs_stats(const double* a, const double* b, uint64_t n, 
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = lb_blocks(n, 4);
     lb_stats_kernel<<<nb, LB_THREADS, 0, st>>>(a, b, n, ws);
-    lb_reduce_kernel<<<1, 64, 0, st>>>(ws, nb, 4, 2ull | 8ull, out4);
+    lb_reduce_kernel<<<1, 32 * LB_RED_WARPS, 0, st>>>(ws, nb, 4, 2ull | 8ull, out4);
     SVGPFA_CHECK_LAUNCH("lbfgs_stats");
     return SVGPFA_OK;
 }
