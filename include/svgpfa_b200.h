@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 6
+#define SVGPFA_ABI_VERSION 7
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -143,6 +143,10 @@ typedef struct svgpfa_buffers {
     /* ---- quadrature statistics ---------------------------------------------------------- */
     double* mu_q;                /* R*Q*K */
     double* var_q;               /* R*Q*K */
+    double* v_q;                 /* R*KM*Q  [r][moff_k + j][q]  OPTIONAL (may be NULL): V = L^-1 kappa(Z, t_q) of every quadrature
+                                    point, written by svgpfa_quad_latent_fwd and read back by svgpfa_quad_latent_bwd instead of
+                                    being rebuilt (M <= 32, Q even; 20.5 GB at config #5).  Must be NULL when the buffers of a
+                                    call do not belong to this Q (post-fit read-outs at other times) */
     double* mubar_part;          /* n_ntiles*R*K*Q  [tile][r][k][q] per-neuron-tile partials of dELBO/dmu_q */
     double* varbar_part;         /* n_ntiles*R*K*Q  same layout                                  */
     double* term1_part;          /* SVGPFA_TERM1_SLOTS partial sums of the intensity integral  */

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -42,7 +42,7 @@ class Dims(C.Structure):
 BUFFER_FIELDS = (
     "desc", "kscale", "theta", "Z", "m", "cholvec", "C", "d", "tq", "wq", "spike_t", "seg_off", "spike_cnt",
     "L", "Li", "X", "c", "alpha", "logdetL", "kl_rk", "A_q", "abar_q", "abar_spk", "dz_acc", "dth_part",
-    "mu_q", "var_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "pm_tau", "pm_mun", "pm_mt", "mu_s", "gsum",
+    "mu_q", "var_q", "v_q", "mubar_part", "varbar_part", "term1_part", "fin_part", "pm_tau", "pm_mun", "pm_mt", "mu_s", "gsum",
     "shared", "gZ", "gm", "gcholvec", "info")
 
 

@@ -47,7 +47,11 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 // the groups are dealt to the warps as evenly as possible (Q = 200: 25 groups -> 7, 6, 6, 6) and a warp covers its
 // share in passes of 4 or 3 groups (7 -> 4 + 3, 6 -> 3 + 3): two instantiations of the pass body, no idle warp, at
 // most two padded groups per warp.
-template <int MT, bool BWD>
+// VC ("V cache"): V = Li K of every quadrature point goes to HBM in the forward kernel (buffers.v_q, R KM Q doubles) and
+// is read back by the adjoint instead of being rebuilt there: the adjoint then needs neither the kernel values at the
+// points (abar = sum_q mubar_q k_q = L sum_q mubar_q v_q, one M x M matrix-vector product per CTA at the end) nor the
+// V product -- 20 of its 92 mma per 8 points and one of its two sets of kernel evaluations.
+template <int MT, bool BWD, bool VC>
 __global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 3 : 4)
 quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
@@ -119,6 +123,13 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
     bool first_pass = true;
+    if (BWD && VC && lane < M) {                                     // this warp's first V rows towards L2 (see prefetch_v)
+        const int G0 = (dm.Q + 7) / 8, base0 = G0 / nw, rem0 = G0 - base0 * nw;
+        const int q0 = 8 * (warp * base0 + (warp < rem0 ? warp : rem0));
+        const double* vrow = bf.v_q + (((size_t)r * dm.KM + ds.moff + lane) * dm.Q + q0);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + 16));
+    }
     if (need_kz) {
         // G = X X^T - I in place of X (X itself is not needed by the adjoint): W = X X^T v - v = G v is ONE full product
         // (2 MT k-steps x NQT mma per row tile) instead of U = X^T V followed by W = X U - V (two triangular ones, a tile
@@ -161,10 +172,37 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     }
 
     // ---- one pass over NQT groups (8 NQT <= 32 points) starting at point qbase
-    auto run_pass = [&](auto nqt_tag, const int qbase, const int qend) {
+    // L2 prefetch of the V rows of a pass starting at point qb (V cache, adjoint): lane <-> row, two 128-byte lines each
+    auto prefetch_v = [&](int qb) {
+        if (BWD && VC && qb >= 0 && lane < M) {
+            const double* vrow = bf.v_q + (((size_t)r * dm.KM + ds.moff + lane) * dm.Q + qb);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + 16));
+        }
+    };
+    auto run_pass = [&](auto nqt_tag, const int qbase, const int qend, const int next_qbase) {
         constexpr int NQT = decltype(nqt_tag)::value;
         constexpr int NPT = 8 * NQT;
         const int q_lane = qbase + lane;
+        if (BWD && VC) {
+            // the tile receives V straight from HBM: 16-byte asynchronous copies, two rows per instruction, zero fill for
+            // rows >= M and points past the pass; all of them in flight at once, awaited below together with the
+            // partial sums -- and the next pass's rows are pulled into L2 meanwhile
+            const double* vg = bf.v_q + ((size_t)r * dm.KM + ds.moff) * dm.Q;
+            const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tileV);
+            const int half = lane >> 4, cl = lane & 15, col = qbase + 2 * cl;
+            const bool colok = 2 * cl < NPT && col < qend;
+#pragma unroll 4
+            for (int j0 = 0; j0 < MP; j0 += 2) {
+                const int j = j0 + half;
+                const bool ok = colok && j < M;
+                const double* src = vg + (ok ? (size_t)j * dm.Q + col : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + (unsigned)(j * LDT + 2 * cl) * 8u), "l"(src),
+                             "r"(ok ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            prefetch_v(next_qbase);
+        }
         const bool valid = lane < NPT && q_lane < qend;       // qend: end of this warp's share (a padded group belongs
                                                               // to the next warp) and of the trial's points
         const double t_lane = valid ? bf.tq[(size_t)r * dm.Q + q_lane] : 0.0;
@@ -178,18 +216,23 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         }
         // ---- kernel values K[j][q], lane <-> point, four inducing points per iteration -> tileK.
         //      FWD: mu_q = k_q . alpha falls out of the same loop without any cross-lane reduction.
+        //      BWD with the V cache: the tile receives V straight from HBM (rows >= M and points past the pass are zero).
         double mu_lane = 0.0;
+        if (BWD && VC) {
+            // (V is on its way into the tile, see the top of the pass)
+        } else {
 #pragma unroll 1
-        for (int j0 = 0; j0 < MP; j0 += 4) {
-            double dl[4], kv[4], qq[4], s2x[4];
+            for (int j0 = 0; j0 < MP; j0 += 4) {
+                double dl[4], kv[4], qq[4], s2x[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dl[e] = t_lane - zs[j0 + e];
-            kappa_vals_n<4>(kc, dl, etab, sctab, kv, qq, s2x);
+                for (int e = 0; e < 4; ++e) dl[e] = t_lane - zs[j0 + e];
+                kappa_vals_n<4>(kc, dl, etab, sctab, kv, qq, s2x);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double v = (valid && j0 + e < M) ? kv[e] : 0.0;
-                tileK[(j0 + e) * LDT + lane] = v;
-                if (!BWD) mu_lane = fma(v, al[j0 + e], mu_lane);
+                for (int e = 0; e < 4; ++e) {
+                    const double v = (valid && j0 + e < M) ? kv[e] : 0.0;
+                    tileK[(j0 + e) * LDT + lane] = v;
+                    if (!BWD) mu_lane = fma(v, al[j0 + e], mu_lane);
+                }
             }
         }
         if (BWD) {
@@ -203,6 +246,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             }
             mbs[lane] = mbar;
             vbs[lane] = vbar;
+            if (VC) asm volatile("cp.async.wait_all;" ::: "memory");
         } else if (valid) {
             bf.mu_q[((size_t)r * dm.Q + q_lane) * dm.K + k] = mu_lane;
         }
@@ -226,23 +270,36 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             __syncthreads();
             first_pass = false;
         }
-        // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]
+        // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]     (BWD with the V cache: already in the tile)
         double v[MT][NQT][2];
+        if (!(BWD && VC)) {
 #pragma unroll
-        for (int rt = 0; rt < MT; ++rt)
+            for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
-            for (int qt = 0; qt < NQT; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
+                for (int qt = 0; qt < NQT; ++qt) v[rt][qt][0] = v[rt][qt][1] = 0.0;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            double b[NQT];
+            for (int ks = 0; ks < KS; ++ks) {
+                double b[NQT];
 #pragma unroll
-            for (int qt = 0; qt < NQT; ++qt) b[qt] = tileK[(4 * ks + tg) * LDT + 8 * qt + g];
+                for (int qt = 0; qt < NQT; ++qt) b[qt] = tileK[(4 * ks + tg) * LDT + 8 * qt + g];
 #pragma unroll
-            for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
-                const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
+                for (int rt = ks / 2; rt < MT; ++rt) {               // Li lower-triangular: k-step ks feeds row tiles >= ks/2
+                    const double a = Lis[(8 * rt + g) * LD + 4 * ks + tg];
 #pragma unroll
-                for (int qt = 0; qt < NQT; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, b[qt]);
+                    for (int qt = 0; qt < NQT; ++qt) dmma(v[rt][qt][0], v[rt][qt][1], a, b[qt]);
+                }
             }
+        }
+        if (!BWD && VC) {                                            // the forward kernel feeds the cache from the fragments
+            double* vg = bf.v_q + ((size_t)r * dm.KM + ds.moff) * dm.Q;
+#pragma unroll
+            for (int rt = 0; rt < MT; ++rt)
+#pragma unroll
+                for (int qt = 0; qt < NQT; ++qt) {
+                    const int row = 8 * rt + g, col = qbase + 8 * qt + 2 * tg;       // Q is even: pairs never straddle qend
+                    if (row < M && col < qend)
+                        __stcs(reinterpret_cast<double2*>(vg + (size_t)row * dm.Q + col), make_double2(v[rt][qt][0], v[rt][qt][1]));
+                }
         }
         if (!BWD) {
             double vv[NQT][2];
@@ -301,13 +358,15 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                 }
             }
         } else {
-            __syncwarp();                                            // every lane is done reading K (abar loop, V product)
+            if (!VC) {
+                __syncwarp();                                        // every lane is done reading K (abar loop, V product)
 #pragma unroll
-            for (int rt = 0; rt < MT; ++rt)
+                for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
-                for (int qt = 0; qt < NQT; ++qt)
-                    *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
-            __syncwarp();
+                    for (int qt = 0; qt < NQT; ++qt)
+                        *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
+                __syncwarp();
+            }
             // ---- A += V diag(varbar) V^T over the points of the pass: k-step = 4 points, A/B fragments from the V tile
 #pragma unroll
             for (int ks = 0; ks < 2 * NQT; ++ks) {
@@ -421,8 +480,10 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         int n4 = share - 3 * np;                                     // passes of four groups; the rest take three
         if (n4 < 0) n4 = 0;
         for (int p = 0; p < np; ++p) {
-            if (p < n4) { run_pass(std::integral_constant<int, 4>{}, 8 * gstart, qend); gstart += 4; }
-            else { run_pass(std::integral_constant<int, 3>{}, 8 * gstart, qend); gstart += 3; }
+            const int step = p < n4 ? 4 : 3, nxt = p + 1 < np ? 8 * (gstart + step) : -1;
+            if (p < n4) run_pass(std::integral_constant<int, 4>{}, 8 * gstart, qend, nxt);
+            else run_pass(std::integral_constant<int, 3>{}, 8 * gstart, qend, nxt);
+            gstart += step;
         }
     }
     if (!BWD) return;
@@ -456,14 +517,33 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         if (i < M && j <= i) bf.A_q[mo + (size_t)i * M + j] = s;
     }
     const size_t vo = (size_t)r * dm.KM + ds.moff;
-    if (tid < M) {
+    if (VC) {                                                        // L over Li (no longer needed) for abar = L vm below
+        for (int idx = tid; idx < MP * MP; idx += blockDim.x) {
+            const int i = idx / MP, j = idx - i * MP;
+            Lis[i * LD + j] = (i < M && j <= i) ? bf.L[mo + (size_t)i * M + j] : 0.0;
+        }
+    }
+    if (tid < MP) {
         double sa = 0.0, sz = 0.0;
         for (int w = 0; w < nw; ++w) {
             sa += t0p[(size_t)w * WSTRIDE + NTA * 64 + tid];
             sz += t0p[(size_t)w * WSTRIDE + NTA * 64 + MP + tid];
         }
-        bf.abar_q[vo + tid] = sa;
-        if (need_kz) atomicAdd(bf.dz_acc + vo + tid, sz);             // zeroed by the caller; the spike kernel adds too
+        if (VC) al[tid] = sa;                                        // vm = sum_q mubar_q v_q
+        else if (tid < M) bf.abar_q[vo + tid] = sa;
+        if (need_kz && tid < M) atomicAdd(bf.dz_acc + vo + tid, sz);  // zeroed by the caller; the spike kernel adds too
+    }
+    if (VC) {
+        __syncthreads();
+        if (tid < M) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+            for (int p = 0; p < MP; p += 2) {
+                s0 = fma(Lis[tid * LD + p], al[p], s0);
+                s1 = fma(Lis[tid * LD + p + 1], al[p + 1], s1);
+            }
+            bf.abar_q[vo + tid] = s0 + s1;
+        }
     }
     if (need_kz && (flags & SVGPFA_GRAD_KERNEL)) {
         const double s0 = block_sum(th0, red);
@@ -476,8 +556,8 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     }
 }
 
-template <int MT, bool BWD>
-void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+template <int MT, bool BWD, bool VC>
+void launch_qm_vc(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
     const int G = (dims->Q + 7) / 8;                    // 8-point groups
     int nw = (G + 3) / 4;                               // a warp takes up to four groups before another one is added
     int cap = dims->quad_warps > 0 ? dims->quad_warps : QM_MAX_WARPS;
@@ -485,8 +565,15 @@ void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flag
     if (nw > cap) nw = cap;
     if (nw < 1) nw = 1;
     const size_t smem = sizeof(double) * qm_smem_doubles(8 * MT, nw, BWD);
-    SVGPFA_ENSURE_SMEM(sizeof(double) * qm_smem_doubles(8 * MT, QM_MAX_WARPS, BWD), quad_latent_mma_kernel<MT, BWD>);
-    quad_latent_mma_kernel<MT, BWD><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
+    SVGPFA_ENSURE_SMEM(sizeof(double) * qm_smem_doubles(8 * MT, QM_MAX_WARPS, BWD), quad_latent_mma_kernel<MT, BWD, VC>);
+    quad_latent_mma_kernel<MT, BWD, VC><<<dim3(svgpfa_ntrials(dims), dims->K), 32 * nw, smem, st>>>(*dims, *buf, flags);
+}
+
+template <int MT, bool BWD>
+void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    // the V cache: buffers.v_q given, pairs of points 16-byte aligned (Q even)
+    if (buf->v_q && (dims->Q & 1) == 0) launch_qm_vc<MT, BWD, true>(dims, buf, flags, st);
+    else launch_qm_vc<MT, BWD, false>(dims, buf, flags, st);
 }
 
 // ======================================================================================

@@ -161,6 +161,7 @@ class B200SVLowerBound:
         if shard_mode not in ("auto", "reduce", "local"):
             raise ValueError("shard_mode must be 'auto', 'reduce' or 'local'")
         self.shard_mode = shard_mode
+        self.v_cache = True               # False: the quadrature adjoint rebuilds V instead of reading it back (saves R*KM*Q*8 bytes)
         self._check_errors = check_errors
         self._pending = []                 # slots of the header copies in flight, oldest first
         self._pinned = None
@@ -400,6 +401,13 @@ class B200SVLowerBound:
             fin_part=torch.zeros(3 * _cabi.FIN_SLOTS, dtype=_F64, device=dev),
             gsum=torch.zeros(max(N * K, 1), dtype=_F64, device=dev),
             info=torch.zeros(4, dtype=torch.int32, device=dev))
+        # V = L^-1 kappa(Z, t_q) of every quadrature point, handed from the forward to the adjoint quadrature kernel
+        # (include/svgpfa_b200.h: buffers.v_q) when it fits comfortably: 20.5 GB at config #5
+        vq_bytes = 8 * R * self._KM * Q
+        if getattr(self, "v_cache", True) and max(self._M) <= 32 and Q % 2 == 0 and vq_bytes > 0:
+            free, _ = torch.cuda.mem_get_info(dev)
+            if vq_bytes <= 0.4 * free:
+                ws["v_q"] = e(R * self._KM * Q)
         self._ws = ws
         self._shared_len = _cabi.SHARED_HDR + N * K + N + self._TH
         dims = _cabi.Dims(R=R, N=N, K=K, Q=Q, KM=self._KM, MM=self._MM, PP=self._PP, TH=self._TH,
@@ -711,6 +719,7 @@ class B200SVLowerBound:
             # the kernels index these arrays by the GLOBAL trial number: bias the pointers by the block's first trial
             b.tq = t.data_ptr() - 8 * r0 * T
             b.mu_q, b.var_q = mu.data_ptr() - 8 * r0 * T * K, var.data_ptr() - 8 * r0 * T * K
+            b.v_q = None                                       # the V cache belongs to the quadrature grid
             with torch.cuda.device(dev):
                 _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(dims), ctypes.byref(b), self._stream()))
             var = var.view(n, T, K)
@@ -820,6 +829,7 @@ class B200SVLowerBound:
         dims.Q = T
         b = _cabi.Buffers.from_buffer_copy(self._bufs)
         b.tq, b.mu_q, b.var_q = t.data_ptr(), mu.data_ptr(), var.data_ptr()
+        b.v_q = None                                           # the V cache belongs to the quadrature grid
         lib = _cabi.lib()
         out = [mu.view(self._R, T, self._K), var.view(self._R, T, self._K)]
         with torch.cuda.device(dev):
