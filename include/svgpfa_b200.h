@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SVGPFA_ABI_VERSION 7
+#define SVGPFA_ABI_VERSION 8
 #define SVGPFA_MAX_M 64            /* inducing points per latent (north_star: M up to 64) */
 
 enum { SVGPFA_KERNEL_EXPQUAD = 0, SVGPFA_KERNEL_PERIODIC = 1 };
@@ -54,7 +54,8 @@ enum {
     SVGPFA_GRAD_ALL       = 15,
     SVGPFA_REUSE_KZZ      = 16,    /* L, Li, logdet already valid for the current (Z, theta)   */
     SVGPFA_REUSE_SPIKE    = 32,    /* abar_spk already valid for the current (Z, theta, C)     */
-    SVGPFA_REBUILD_PANELS = 64     /* spike_method = PANEL: rebuild pm_tau for the trial range first (new spikes) */
+    SVGPFA_REBUILD_PANELS = 64,    /* spike_method = PANEL: rebuild pm_tau for the trial range first (new spikes) */
+    SVGPFA_REUSE_VQ       = 128    /* buffers.v_q already valid for the current (Z, theta): every E-step closure after the first */
 };
 
 /* How the spike-time term is evaluated (svgpfa_dims.spike_method).
@@ -194,6 +195,10 @@ int svgpfa_indpoints_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, voi
  * SVPosteriorOnLatentsAllTimes.__computeMeansAndVarsGivenKernelMatrices (svPosteriorOnLatents.py:185-216);
  * Ktz (R,Q,M) is never materialised. */
 int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
+/* the same from buffers.v_q (V = L^-1 kappa(Z, t_q), written by an earlier svgpfa_quad_latent_fwd for the same Z, theta):
+ * mu_q = v_q . c, var_q = s2 - |v_q|^2 + |X^T v_q|^2 -- no kernel evaluation (svgpfa_elbo_grad with SVGPFA_REUSE_VQ);
+ * falls back to svgpfa_quad_latent_fwd when the cache does not apply */
+int svgpfa_quad_latent_fwd_cached(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream);
 
 /* (iii) embedding + exp-link intensity integral + its adjoints (dC, dd into `shared`, mubar/varbar partials).
  * Replaces LinearSVEmbeddingAllTimes._computeMeansAndVarsGivenSVPosteriorOnLatentsStats (svEmbedding.py:80-84),

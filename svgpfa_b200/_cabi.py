@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsvgpfa_b200.so")
 PROBES_LIB_PATH = os.path.join(PKG, "libsvgpfa_b200_probes.so")      # measurement probes / test hooks, not product
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_M = 64
 EMBED_TN = 128
 SHARED_HDR = 8
@@ -22,7 +22,7 @@ SHARED_STATUS = 5            # shared[5..7] = (status, trial, latent) of a faile
 KERNEL_EXPQUAD, KERNEL_PERIODIC = 0, 1
 GRAD_POSTERIOR, GRAD_EMBEDDING, GRAD_KERNEL, GRAD_INDLOCS = 1, 2, 4, 8
 GRAD_ALL = 15
-REUSE_KZZ, REUSE_SPIKE, REBUILD_PANELS = 16, 32, 64
+REUSE_KZZ, REUSE_SPIKE, REBUILD_PANELS, REUSE_VQ = 16, 32, 64, 128
 SPIKE_DIRECT, SPIKE_PANEL = 1, 2
 PM_P = 16
 INFO_NOT_PD = 1
@@ -67,6 +67,7 @@ SYMBOLS = {
     "svgpfa_kzz_chol_fwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_indpoints_fwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_quad_latent_fwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
+    "svgpfa_quad_latent_fwd_cached": (C.c_int, [_P(Dims), _P(Buffers), C.c_void_p]),
     "svgpfa_quad_embed_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_quad_latent_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),
     "svgpfa_spike_fwd_bwd": (C.c_int, [_P(Dims), _P(Buffers), C.c_uint32, C.c_void_p]),

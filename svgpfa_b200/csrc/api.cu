@@ -207,7 +207,8 @@ int run_trial_stages(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_
     if (mark) stage_mark(1 + SVGPFA_STAGE_KZZ_CHOL, st);
     if (!fused) { rc = svgpfa_indpoints_fwd(dims, buf, stream); if (rc) return rc; }
     if (mark) stage_mark(1 + SVGPFA_STAGE_INDPOINTS_FWD, st);
-    rc = svgpfa_quad_latent_fwd(dims, buf, stream); if (rc) return rc;
+    rc = (flags & SVGPFA_REUSE_VQ) ? svgpfa_quad_latent_fwd_cached(dims, buf, stream) : svgpfa_quad_latent_fwd(dims, buf, stream);
+    if (rc) return rc;
     if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_LATENT_FWD, st);
     rc = svgpfa_quad_embed_fwd_bwd(dims, buf, flags, stream); if (rc) return rc;
     if (mark) stage_mark(1 + SVGPFA_STAGE_QUAD_EMBED, st);
@@ -350,7 +351,7 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
     if (!dims->desc_host) return svgpfa_set_error(SVGPFA_E_ARG, "elbo_grad_host: dims.desc_host", cudaSuccess);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t R = dims->R, D = sizeof(double);
-    uint32_t flags_run = flags & ~(uint32_t)(SVGPFA_REUSE_KZZ | SVGPFA_REUSE_SPIKE);   // every input is new
+    uint32_t flags_run = flags & ~(uint32_t)(SVGPFA_REUSE_KZZ | SVGPFA_REUSE_SPIKE | SVGPFA_REUSE_VQ);   // every input is new
     if (io->copy_static && dims->spike_method == SVGPFA_SPIKE_PANEL) flags_run |= SVGPFA_REBUILD_PANELS;   // new spikes
 #define CPY(dst, src, bytes, kind, s_)                                                                \
     do {                                                                                              \

@@ -624,6 +624,17 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
     return SVGPFA_OK;
 }
 
+// forward with V of every quadrature point still valid in buffers.v_q (same Z, theta as the call that wrote it)
+extern "C" int svgpfa_quad_latent_fwd_cached(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
+    if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd_cached", cudaSuccess);
+    if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
+    if (buf->v_q && use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, SVGPFA_REUSE_VQ, false, (cudaStream_t)stream)) {
+        SVGPFA_CHECK_LAUNCH("quad_latent_fwd_cached (mma)");
+        return SVGPFA_OK;
+    }
+    return svgpfa_quad_latent_fwd(dims, buf, stream);
+}
+
 extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;

@@ -51,9 +51,13 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 // is read back by the adjoint instead of being rebuilt there: the adjoint then needs neither the kernel values at the
 // points (abar = sum_q mubar_q k_q = L sum_q mubar_q v_q, one M x M matrix-vector product per CTA at the end) nor the
 // V product -- 20 of its 92 mma per 8 points and one of its two sets of kernel evaluations.
-template <int MT, bool BWD, bool VC>
+// VM = 0: no cache; 1: forward writes it, adjoint reads it; 2 (forward only): V is still valid for the current (Z, theta)
+// -- every E-step closure after the first -- and the forward kernel reads it too: no kernel evaluation and no V product
+// at all, mu_q = v_q . c (c = Li m), var_q = s2 - |v_q|^2 + |X^T v_q|^2.
+template <int MT, bool BWD, int VM>
 __global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 3 : 4)
 quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+    constexpr bool VC = VM >= 1, RV = !BWD && VM == 2, LOADV = VC && (BWD || RV);
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
@@ -110,7 +114,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         const size_t vo = (size_t)r * dm.KM + ds.moff;
         for (int i = tid; i < MP; i += blockDim.x) {
             zs[i] = (i < M) ? zg[i] : 0.0;
-            al[i] = (i < M) ? bf.alpha[vo + i] : 0.0;
+            al[i] = (i < M) ? (RV ? bf.c[vo + i] : bf.alpha[vo + i]) : 0.0;       // RV: mu = v . c
         }
     }
     __syncthreads();
@@ -123,7 +127,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     const double zj_own = zs[lane < MP ? lane : 0], aj_own = al[lane < MP ? lane : 0];
     const size_t part_stride = (size_t)dm.R * dm.K * dm.Q;
     bool first_pass = true;
-    if (BWD && VC && lane < M) {                                     // this warp's first V rows towards L2 (see prefetch_v)
+    if (LOADV && lane < M) {                                         // this warp's first V rows towards L2 (see prefetch_v)
         const int G0 = (dm.Q + 7) / 8, base0 = G0 / nw, rem0 = G0 - base0 * nw;
         const int q0 = 8 * (warp * base0 + (warp < rem0 ? warp : rem0));
         const double* vrow = bf.v_q + (((size_t)r * dm.KM + ds.moff + lane) * dm.Q + q0);
@@ -174,7 +178,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     // ---- one pass over NQT groups (8 NQT <= 32 points) starting at point qbase
     // L2 prefetch of the V rows of a pass starting at point qb (V cache, adjoint): lane <-> row, two 128-byte lines each
     auto prefetch_v = [&](int qb) {
-        if (BWD && VC && qb >= 0 && lane < M) {
+        if (LOADV && qb >= 0 && lane < M) {
             const double* vrow = bf.v_q + (((size_t)r * dm.KM + ds.moff + lane) * dm.Q + qb);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + 16));
@@ -184,7 +188,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         constexpr int NQT = decltype(nqt_tag)::value;
         constexpr int NPT = 8 * NQT;
         const int q_lane = qbase + lane;
-        if (BWD && VC) {
+        if (LOADV) {
             // the tile receives V straight from HBM: 16-byte asynchronous copies, two rows per instruction, zero fill for
             // rows >= M and points past the pass; all of them in flight at once, awaited below together with the
             // partial sums -- and the next pass's rows are pulled into L2 meanwhile
@@ -217,8 +221,8 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         // ---- kernel values K[j][q], lane <-> point, four inducing points per iteration -> tileK.
         //      FWD: mu_q = k_q . alpha falls out of the same loop without any cross-lane reduction.
         //      BWD with the V cache: the tile receives V straight from HBM (rows >= M and points past the pass are zero).
-        double mu_lane = 0.0;
-        if (BWD && VC) {
+        double mu_lane = 0.0, vv_lane = 0.0;
+        if (LOADV) {
             // (V is on its way into the tile, see the top of the pass)
         } else {
 #pragma unroll 1
@@ -247,8 +251,23 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             mbs[lane] = mbar;
             vbs[lane] = vbar;
             if (VC) asm volatile("cp.async.wait_all;" ::: "memory");
-        } else if (valid) {
-            bf.mu_q[((size_t)r * dm.Q + q_lane) * dm.K + k] = mu_lane;
+        } else {
+            if (RV) {                                 // mu_q = v_q . c and |v_q|^2, lane <-> point
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                double m0 = 0.0, m1 = 0.0, w0 = 0.0, w1 = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < MP; j += 2) {
+                    const double x0 = tileV[j * LDT + lane], x1 = tileV[(j + 1) * LDT + lane];
+                    m0 = fma(x0, al[j], m0);
+                    m1 = fma(x1, al[j + 1], m1);
+                    w0 = fma(x0, x0, w0);
+                    w1 = fma(x1, x1, w1);
+                }
+                mu_lane = m0 + m1;
+                vv_lane = w0 + w1;
+            }
+            if (valid) bf.mu_q[((size_t)r * dm.Q + q_lane) * dm.K + k] = mu_lane;
         }
         __syncwarp();
         if (BWD && lane < MP) {
@@ -272,7 +291,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         }
         // ---- V = Li K      v[rt][qt] = V[8 rt + g][8 qt + 2 tg + {0,1}]     (BWD with the V cache: already in the tile)
         double v[MT][NQT][2];
-        if (!(BWD && VC)) {
+        if (!LOADV) {
 #pragma unroll
             for (int rt = 0; rt < MT; ++rt)
 #pragma unroll
@@ -290,7 +309,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
                 }
             }
         }
-        if (!BWD && VC) {                                            // the forward kernel feeds the cache from the fragments
+        if (!BWD && VM == 1) {                                       // the forward kernel feeds the cache from the fragments
             double* vg = bf.v_q + ((size_t)r * dm.KM + ds.moff) * dm.Q;
 #pragma unroll
             for (int rt = 0; rt < MT; ++rt)
@@ -303,22 +322,24 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         }
         if (!BWD) {
             double vv[NQT][2];
+            if (!RV) {
 #pragma unroll
-            for (int qt = 0; qt < NQT; ++qt) {
-                vv[qt][0] = vv[qt][1] = 0.0;
+                for (int qt = 0; qt < NQT; ++qt) {
+                    vv[qt][0] = vv[qt][1] = 0.0;
 #pragma unroll
-                for (int rt = 0; rt < MT; ++rt) {
-                    vv[qt][0] = fma(v[rt][qt][0], v[rt][qt][0], vv[qt][0]);
-                    vv[qt][1] = fma(v[rt][qt][1], v[rt][qt][1], vv[qt][1]);
+                    for (int rt = 0; rt < MT; ++rt) {
+                        vv[qt][0] = fma(v[rt][qt][0], v[rt][qt][0], vv[qt][0]);
+                        vv[qt][1] = fma(v[rt][qt][1], v[rt][qt][1], vv[qt][1]);
+                    }
                 }
+                __syncwarp();                                        // every lane is done reading K (same tile)
+#pragma unroll
+                for (int rt = 0; rt < MT; ++rt)
+#pragma unroll
+                    for (int qt = 0; qt < NQT; ++qt)
+                        *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
+                __syncwarp();
             }
-            __syncwarp();                                            // every lane is done reading K (same tile)
-#pragma unroll
-            for (int rt = 0; rt < MT; ++rt)
-#pragma unroll
-                for (int qt = 0; qt < NQT; ++qt)
-                    *reinterpret_cast<double2*>(tileV + (8 * rt + g) * LDT + 8 * qt + 2 * tg) = make_double2(v[rt][qt][0], v[rt][qt][1]);
-            __syncwarp();
             // ---- U = X^T V     u[jt][qt] = U[8 jt + g][8 qt + 2 tg + {0,1}]
             double u[MT][NQT][2];
 #pragma unroll
@@ -340,7 +361,15 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             // var = s2 - ||v||^2 + ||u||^2 : column sums over the 8 row groups
 #pragma unroll
             for (int qt = 0; qt < NQT; ++qt) {
-                double d0 = -vv[qt][0], d1 = -vv[qt][1];
+                double d0, d1;
+                if (RV) {                             // |v|^2 of columns 8 qt + 2 tg + {0, 1}: the full sums, subtracted once
+                    d0 = -__shfl_sync(0xffffffffu, vv_lane, 8 * qt + 2 * tg);
+                    d1 = -__shfl_sync(0xffffffffu, vv_lane, 8 * qt + 2 * tg + 1);
+                    if (g != 0) d0 = d1 = 0.0;
+                } else {
+                    d0 = -vv[qt][0];
+                    d1 = -vv[qt][1];
+                }
 #pragma unroll
                 for (int jt = 0; jt < MT; ++jt) {
                     d0 = fma(u[jt][qt][0], u[jt][qt][0], d0);
@@ -556,7 +585,7 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     }
 }
 
-template <int MT, bool BWD, bool VC>
+template <int MT, bool BWD, int VC>
 void launch_qm_vc(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
     const int G = (dims->Q + 7) / 8;                    // 8-point groups
     int nw = (G + 3) / 4;                               // a warp takes up to four groups before another one is added
@@ -572,8 +601,10 @@ void launch_qm_vc(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t f
 template <int MT, bool BWD>
 void launch_qm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
     // the V cache: buffers.v_q given, pairs of points 16-byte aligned (Q even)
-    if (buf->v_q && (dims->Q & 1) == 0) launch_qm_vc<MT, BWD, true>(dims, buf, flags, st);
-    else launch_qm_vc<MT, BWD, false>(dims, buf, flags, st);
+    if (buf->v_q && (dims->Q & 1) == 0) {
+        if (!BWD && (flags & SVGPFA_REUSE_VQ)) launch_qm_vc<MT, false, 2>(dims, buf, flags, st);
+        else launch_qm_vc<MT, BWD, 1>(dims, buf, flags, st);
+    } else launch_qm_vc<MT, BWD, 0>(dims, buf, flags, st);
 }
 
 // ======================================================================================

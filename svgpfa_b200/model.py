@@ -178,7 +178,7 @@ class B200SVLowerBound:
         self._spikes_set = False
         self._quad_set = False
         self._ready = False
-        self._kzz_key = None
+        self._kzz_key = self._vq_key = None
         self._spike_key = None
         self._bufs = None
         if kernels is not None:
@@ -203,7 +203,7 @@ class B200SVLowerBound:
     def setKernels(self, kernels):
         self._kernels = list(kernels)
         self._ready = False
-        self._kzz_key = self._spike_key = None
+        self._kzz_key = self._spike_key = self._vq_key = None
         if self._params_set:               # kernels replaced after the parameters: re-derive what depends on them
             if len(self._kernels) != self._K:
                 raise ValueError("inconsistent number of latents in kernels / initial_params")
@@ -289,7 +289,7 @@ class B200SVLowerBound:
         self._refresh_leaf_list()
         self._params_set = True
         self._ready = False
-        self._kzz_key = self._spike_key = None
+        self._kzz_key = self._spike_key = self._vq_key = None
 
     def setMeasurements(self, measurements):
         """``measurements[r][n]`` = spike times of neuron n in trial r (list / array / tensor, float32
@@ -343,7 +343,7 @@ class B200SVLowerBound:
 
     def setPriorCovRegParam(self, priorCovRegParam):
         self._reg = float(priorCovRegParam)
-        self._kzz_key = self._spike_key = None
+        self._kzz_key = self._spike_key = self._vq_key = None
         if self._ready:
             self._dims.reg = self._reg         # the value the kernels read
 
@@ -430,7 +430,7 @@ class B200SVLowerBound:
         self._pm = None
         self._gsum_key = None
         self._ready = True
-        self._kzz_key = self._spike_key = None
+        self._kzz_key = self._spike_key = self._vq_key = None
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self._dev()).cuda_stream)
@@ -442,7 +442,7 @@ class B200SVLowerBound:
     def buildKernelsMatrices(self):
         """Reference semantics (svLowerBound.py:77-78): everything derived from (theta, Z) is
         recomputed from their current values at the next evaluation."""
-        self._kzz_key = None
+        self._kzz_key = self._vq_key = None
         self._spike_key = None
 
     # ------------------------------------------------------------------ spike-term method (include/svgpfa_b200.h)
@@ -526,6 +526,9 @@ class B200SVLowerBound:
         call_flags = flags
         if self._kzz_key == kz_key:
             call_flags |= _cabi.REUSE_KZZ
+        has_vq = "v_q" in self._ws
+        if has_vq and getattr(self, "_vq_key", None) == kz_key:
+            call_flags |= _cabi.REUSE_VQ             # V of the quadrature points depends on (Z, theta) only: E-step closures
         if self._spike_key == sp_key and not (flags & (_cabi.GRAD_KERNEL | _cabi.GRAD_INDLOCS | _cabi.GRAD_EMBEDDING)):
             call_flags |= _cabi.REUSE_SPIKE
         b = self._bufs
@@ -543,6 +546,7 @@ class B200SVLowerBound:
             _cabi.check(_cabi.lib().svgpfa_elbo_grad(ctypes.byref(self._dims), ctypes.byref(b),
                                                      call_flags, self._stream()), "elbo_grad")
         self._kzz_key, self._spike_key = kz_key, sp_key
+        self._vq_key = kz_key if has_vq else None
         self._finish(shared, flags)
         return shared, gZ, gm, gcv
 
@@ -591,7 +595,7 @@ class B200SVLowerBound:
             hdr = self._pinned[slot]
             if float(hdr[_cabi.SHARED_STATUS]) > 0.0:
                 self._pending.clear()
-                self._kzz_key = self._spike_key = None
+                self._kzz_key = self._spike_key = self._vq_key = None
                 where = (f"Kzz of trial {int(hdr[6])}, latent {int(hdr[7])} is" if float(hdr[_cabi.SHARED_STATUS]) == 1.0
                          else "a Kzz of more than one trial shard is")
                 raise torch.linalg.LinAlgError(f"linalg.cholesky: {where} not positive-definite")
@@ -664,7 +668,7 @@ class B200SVLowerBound:
                 sharding.all_reduce_shared(shared, self._pg)
                 io["shared"].copy_(shared, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-        self._kzz_key = self._spike_key = None
+        self._kzz_key = self._spike_key = self._vq_key = None
         if self._pm is not None:
             self._pm["theta_version"] = None        # the device parameters were replaced: re-derive at the next eval()
         nb = lambda *names: sum(io[n].numel() * io[n].element_size() for n in names)
@@ -750,6 +754,7 @@ class B200SVLowerBound:
                 self._kzz_key = kz_key
             _cabi.check(lib.svgpfa_indpoints_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
             _cabi.check(lib.svgpfa_quad_latent_fwd(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
+            self._vq_key = kz_key if "v_q" in self._ws else None
             if panel:
                 _cabi.check(lib.svgpfa_panel_neuron_sums(ctypes.byref(self._dims), ctypes.byref(b), self._stream()))
         R, Q, K = self._R, self._Q, self._K
@@ -849,7 +854,7 @@ class B200SVLowerBound:
                 shape = (self._R, T, self._N)
                 out += [None if x is None else x.view(shape) for x in (em, ev, cif)]
         if self._check_errors and int(self._ws["info"][0].item()) == _cabi.INFO_NOT_PD:
-            self._kzz_key = None
+            self._kzz_key = self._vq_key = None
             raise torch.linalg.LinAlgError("linalg.cholesky: Kzz is not positive-definite")
         return out
 
@@ -881,7 +886,7 @@ class B200SVLowerBound:
         self._poll_errors(block=True)
         st = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT}
         st["_ready"] = False
-        st["_kzz_key"] = st["_spike_key"] = None
+        st["_kzz_key"] = st["_spike_key"] = st["_vq_key"] = None
         if self._params_set:
             st["_leaf_requires_grad"] = [bool(p.requires_grad) for p in self._leaf_list]
         if self._kernels is not None:

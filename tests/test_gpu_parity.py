@@ -475,3 +475,45 @@ def test_post_fit_readouts_match_reference(name):
     assert len(cifs) == R and len(cifs[0]) == N and tuple(cifs[0][0].shape) == (T,)
     cif = np.stack([np.stack([c.cpu().numpy() for c in trial], axis=1) for trial in cifs])
     assert rel_err(cif, ref["cif"]) <= 1e-9
+
+
+def test_v_cache_and_its_reuse_across_estep_closures():
+    """The forward quadrature kernel hands V = L^-1 K(Z, t_q) to the adjoint through buffers.v_q, and while (Z, theta) do
+    not change (the closures of an E-step) the forward kernel reads it back too (SVGPFA_REUSE_VQ): same bound and
+    gradients as a model without the cache, at every step of a short sequence of posterior updates; a change of Z
+    invalidates it."""
+    from svgpfa_b200.testing import model_from_case, set_requires_grad, grads_as_dict
+    case, _ = synthetic.load_case(os.path.join(GOLDEN, "config3_r4.npz"))
+    with_cache = model_from_case(case)
+    without = model_from_case(case)
+    without.v_cache = False
+    without._ready = False
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(4):
+        outs = []
+        for model in (with_cache, without):
+            set_requires_grad(model, posterior=True, embedding=(step == 0), kernels=(step == 0), indlocs=(step == 0))
+            for p in model.getSVPosteriorOnIndPointsParams() + model.getSVEmbeddingParams() + model.getKernelsParams() + \
+                    model.getIndPointsLocs():
+                p.grad = None
+            v = model.eval()
+            v.backward()
+            outs.append((v.item(), grads_as_dict(model)))
+        assert "v_q" in with_cache._ws and "v_q" not in without._ws
+        (va, ga), (vb, gb) = outs
+        assert abs(va - vb) <= ELBO_TOL * abs(vb)
+        for key, g in gb.items():
+            if g is not None:
+                assert rel_err(ga[key], g) <= GRAD_TOL, (step, key)
+        # an E-step-like update of the posterior parameters (same perturbation on both models); Z moves before the last step
+        with torch.no_grad():
+            for pa, pb in zip(with_cache.getSVPosteriorOnIndPointsParams(), without.getSVPosteriorOnIndPointsParams()):
+                d = 0.01 * torch.randn(pa.shape, dtype=pa.dtype, device=pa.device, generator=gen)
+                pa.add_(d)
+                pb.add_(d)
+            if step == 2:
+                for za, zb in zip(with_cache.getIndPointsLocs(), without.getIndPointsLocs()):
+                    za.add_(1e-3)
+                    zb.add_(1e-3)
+                with_cache.buildKernelsMatrices()
+                without.buildKernelsMatrices()

@@ -17,6 +17,9 @@ def main():
     ap.add_argument("--flags", type=int, default=15)
     ap.add_argument("--quad-warps", type=int, default=0)
     ap.add_argument("--spike-chunks", type=int, default=0)
+    ap.add_argument("--keep", action="store_true",
+                    help="no buildKernelsMatrices() between evaluations: the closure of an E-step (Kzz factors, spike-term "
+                         "statistic and the V cache stay valid)")
     args = ap.parse_args()
     import torch
     from svgpfa_b200 import _cabi, synthetic
@@ -38,7 +41,8 @@ def main():
             e.record()
         arr = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in evs])
         lib.svgpfa_set_stage_events(arr)
-        model.buildKernelsMatrices()
+        if not args.keep:
+            model.buildKernelsMatrices()
         if args.flags == 15:
             v = model.eval()
         else:
