@@ -55,7 +55,7 @@ __host__ __device__ inline size_t qm_smem_doubles(int MP, int nw, bool bwd) {
 // -- every E-step closure after the first -- and the forward kernel reads it too: no kernel evaluation and no V product
 // at all, mu_q = v_q . c (c = Li m), var_q = s2 - |v_q|^2 + |X^T v_q|^2.
 template <int MT, bool BWD, int VM>
-__global__ void __launch_bounds__(32 * QM_MAX_WARPS, BWD ? 3 : 4)
+__global__ void __launch_bounds__(32 * QM_MAX_WARPS, (BWD || MT >= 4) ? 3 : 4)      // MT = 4: three CTAs fit an SM's shared memory anyway
 quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
     constexpr bool VC = VM >= 1, RV = !BWD && VM == 2, LOADV = VC && (BWD || RV);
     constexpr int MP = 8 * MT, KS = 2 * MT, LD = MP + 4, LDT = QM_LDT;
@@ -184,7 +184,9 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vrow + 16));
         }
     };
-    auto run_pass = [&](auto nqt_tag, const int qbase, const int qend, const int next_qbase) {
+    // t_pref: this lane's quadrature node of the pass, fetched one pass ahead (ncu: the first use of a node loaded at the
+    // top of its own pass was the kernel's largest long-scoreboard stall)
+    auto run_pass = [&](auto nqt_tag, const int qbase, const int qend, const int next_qbase, double& t_pref) {
         constexpr int NQT = decltype(nqt_tag)::value;
         constexpr int NPT = 8 * NQT;
         const int q_lane = qbase + lane;
@@ -209,7 +211,8 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         }
         const bool valid = lane < NPT && q_lane < qend;       // qend: end of this warp's share (a padded group belongs
                                                               // to the next warp) and of the trial's points
-        const double t_lane = valid ? bf.tq[(size_t)r * dm.Q + q_lane] : 0.0;
+        const double t_lane = valid ? t_pref : 0.0;
+        if (next_qbase >= 0 && next_qbase + lane < qend) t_pref = bf.tq[(size_t)r * dm.Q + next_qbase + lane];
         tt[lane] = t_lane;
         if (BWD && valid) {                          // the partial sums are read after the kernel evaluations (below):
             const size_t o = ((size_t)r * dm.K + k) * dm.Q + q_lane;      // pull them into L1 meanwhile
@@ -508,10 +511,11 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         const int np = (share + 3) / 4;
         int n4 = share - 3 * np;                                     // passes of four groups; the rest take three
         if (n4 < 0) n4 = 0;
+        double t_pref = 8 * gstart + lane < qend ? bf.tq[(size_t)r * dm.Q + 8 * gstart + lane] : 0.0;
         for (int p = 0; p < np; ++p) {
             const int step = p < n4 ? 4 : 3, nxt = p + 1 < np ? 8 * (gstart + step) : -1;
-            if (p < n4) run_pass(std::integral_constant<int, 4>{}, 8 * gstart, qend, nxt);
-            else run_pass(std::integral_constant<int, 3>{}, 8 * gstart, qend, nxt);
+            if (p < n4) run_pass(std::integral_constant<int, 4>{}, 8 * gstart, qend, nxt, t_pref);
+            else run_pass(std::integral_constant<int, 3>{}, 8 * gstart, qend, nxt, t_pref);
             gstart += step;
         }
     }
