@@ -92,7 +92,9 @@ quad_latent_mma_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
         // Li and X are first needed by the V product, after the kernel evaluations of the first pass: when the rows
         // are whole 16-byte chunks (M = MP, even offset) they are fetched with cp.async and awaited there, so the
         // 16 KB of loads run under ~1400 cycles of arithmetic (ncu: the staging was 12-15 % long-scoreboard stalls)
-        if (M == MP && (mo & 1) == 0) {
+        // (the adjoint with the V cache and no kernel / inducing-point gradients -- an E-step closure -- reads neither)
+        if (BWD && VC && !need_kz) {
+        } else if (M == MP && (mo & 1) == 0) {
             const unsigned lis_s = (unsigned)__cvta_generic_to_shared(Lis), xs_s = (unsigned)__cvta_generic_to_shared(Xs);
             for (int c = tid; c < MP * (MP / 2); c += blockDim.x) {
                 const int i = c / (MP / 2), jj = c - i * (MP / 2);
