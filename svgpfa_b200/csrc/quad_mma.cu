@@ -820,6 +820,267 @@ __global__ void __launch_bounds__(EMM_THREADS) quad_embed_mma_kernel(svgpfa_dims
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same stage with the statistics CONCATENATED, for K <= 24 (round 2).  Mu and Var of a point enter every product
+// side by side:  h = d + [Mu | Var] [C^T ; (C^T)^2 / 2]  is ONE product over 2K (one accumulator, ceil(2K/4) k-steps
+// against two products over K + 1 padded to 8 each);  [mubar | varbar] = G [C | C^2/2]  and  G^T [Mu | Var]  have 2K output
+// columns (K = 20: 5 column tiles against 3 + 3).  GEMM B is split over the NEURONS instead of over its output tiles:
+// warp w multiplies the 16 x 16 block of G it has just produced (its own 16 neurons: no block barrier between A and B)
+// into all 2 NC tiles -- 40 mma per warp at K = 20, all warps busy, where 12 tile-units of 32 mma over 8 warps took two
+// rounds -- and the eight partial results meet in shared memory (upper four warps write, lower four add, then every
+// thread sums four and writes the per-neuron-tile partials coalesced).  dd = column sums of G in registers (the ones
+// column is gone).  mma per item and warp: 40 + 40 + 40 against 48 + 64 (critical path) + 48.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t emc_smem_doubles(int NC) {
+    const int KP2 = 8 * NC;
+    return (size_t)KP2 * EMM_TNS + (size_t)EMM_TQ * EMM_TNS + (size_t)KP2 * EMM_LDQ + EMM_TQ + EMM_TN + (size_t)8 * 2 * NC * 64;
+}
+
+template <int NC>      // NC = ceil(2 K / 8) column tiles of the concatenated statistics
+__global__ void __launch_bounds__(EMM_THREADS, 2) quad_embed_cat_kernel(svgpfa_dims dm, svgpfa_buffers bf, uint32_t flags) {
+    constexpr int KP2 = 8 * NC, KS = 2 * NC, TNS = EMM_TNS, LDQ = EMM_LDQ, NTB = 2 * NC;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int K = dm.K, K2 = 2 * dm.K, N = dm.N, Q = dm.Q;
+    double* CC = sm;                               // [KP2][TNS]  rows < K: C^T, rows K .. 2K-1: (C^T)^2 / 2, rest zero
+    double* Gs = CC + (size_t)KP2 * TNS;           // [TQ][TNS]   G = -w exp(h); every warp reads only its own 16 columns
+    double* stT = Gs + (size_t)EMM_TQ * TNS;       // [KP2][LDQ]  rows < K: Mu, rows K .. 2K-1: Var of the item's 16 points
+    double* ws = stT + (size_t)KP2 * LDQ;          // [TQ]
+    double* dvec = ws + EMM_TQ;                    // [TN]
+    double* redB = dvec + EMM_TN;                  // [8 warps][NTB][32][2] partial GEMM-B tiles in fragment layout
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int tile = blockIdx.x, n0 = tile * EMM_TN;
+    const bool need_emb = flags & SVGPFA_GRAD_EMBEDDING;
+    const bool need_lat = flags & (SVGPFA_GRAD_POSTERIOR | SVGPFA_GRAD_KERNEL | SVGPFA_GRAD_INDLOCS);
+    for (int idx = tid; idx < KP2 * EMM_TN; idx += EMM_THREADS) {
+        const int c = idx / EMM_TN, nn = idx - c * EMM_TN;
+        double v = 0.0;
+        if (n0 + nn < N && c < K2) {
+            const double cval = bf.C[(size_t)(n0 + nn) * K + (c < K ? c : c - K)];
+            v = c < K ? cval : 0.5 * cval * cval;
+        }
+        CC[c * TNS + nn] = v;
+    }
+    if (tid < EMM_TN) dvec[tid] = (n0 + tid < N) ? bf.d[n0 + tid] : 0.0;
+    // GEMM C accumulators: warp owns neuron tiles {2 warp, 2 warp + 1} x the NC column tiles of [Mu | Var]
+    double cc[2][NC][2], dsum[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NC; ++b) cc[a][b][0] = cc[a][b][1] = 0.0;
+    double t1 = 0.0;
+    const int qtiles = (Q + EMM_TQ - 1) / EMM_TQ;
+    const int nitems = (dm.rn ? dm.rn : dm.R) * qtiles;
+    const size_t part_off = (size_t)tile * dm.R * K * Q;
+    __syncthreads();
+    constexpr int NPF = (EMM_TQ * KP2 + EMM_THREADS - 1) / EMM_THREADS;
+    double pf[NPF], pf_w = 0.0;
+    auto fetch = [&](int it) {                    // the NEXT item's statistics travel while the current products run
+        const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EMM_TQ;
+#pragma unroll
+        for (int e = 0; e < NPF; ++e) {
+            const int idx = tid + e * EMM_THREADS;
+            const int qq = idx / KP2, c = idx - qq * KP2;
+            const bool v = idx < EMM_TQ * KP2 && (q0 + qq) < Q && c < K2;
+            const size_t o = ((size_t)r * Q + q0 + qq) * K;
+            pf[e] = v ? (c < K ? bf.mu_q[o + c] : bf.var_q[o + c - K]) : 0.0;
+        }
+        if (tid < EMM_TQ) pf_w = (q0 + tid < Q) ? bf.wq[(size_t)r * Q + q0 + tid] : 0.0;
+    };
+    if ((int)blockIdx.y < nitems) fetch(blockIdx.y);
+    for (int it = blockIdx.y; it < nitems; it += gridDim.y) {
+        const int rl = it / qtiles, r = dm.r0 + rl, q0 = (it - rl * qtiles) * EMM_TQ;
+#pragma unroll
+        for (int e = 0; e < NPF; ++e) {
+            const int idx = tid + e * EMM_THREADS;
+            if (idx < EMM_TQ * KP2) {
+                const int qq = idx / KP2, c = idx - qq * KP2;
+                stT[c * LDQ + qq] = pf[e];
+            }
+        }
+        if (tid < EMM_TQ) ws[tid] = pf_w;
+        __syncthreads();
+        if (it + (int)gridDim.y < nitems) fetch(it + gridDim.y);
+        // ---- GEMM A: h[qt][nl] = H[8 qt + g][8 (2 warp + nl) + 2 tg + e] = d + [Mu | Var] CC
+        {
+            double h[2][2][2];
+#pragma unroll
+            for (int nl = 0; nl < 2; ++nl) {
+                const double2 d2 = *reinterpret_cast<const double2*>(dvec + 8 * (2 * warp + nl) + 2 * tg);
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) { h[qt][nl][0] = d2.x; h[qt][nl][1] = d2.y; }
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double a[2], b[2];
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) a[qt] = stT[(4 * ks + tg) * LDQ + 8 * qt + g];
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) b[nl] = CC[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt)
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) dmma(h[qt][nl][0], h[qt][nl][1], a[qt], b[nl]);
+            }
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt) {
+                const double w = ws[8 * qt + g];
+#pragma unroll
+                for (int nl = 0; nl < 2; ++nl) {
+                    const int nn = 8 * (2 * warp + nl) + 2 * tg;
+                    const double w0 = (n0 + nn < N) ? w : 0.0, w1 = (n0 + nn + 1 < N) ? w : 0.0;
+                    const double e0 = w0 * exp(h[qt][nl][0]);
+                    const double e1 = w1 * exp(h[qt][nl][1]);
+                    t1 += e0 + e1;
+                    dsum[nl][0] -= e0;
+                    dsum[nl][1] -= e1;
+                    *reinterpret_cast<double2*>(Gs + (8 * qt + g) * TNS + nn) = make_double2(-e0, -e1);
+                }
+            }
+        }
+        __syncwarp();                             // this warp's 16 columns of G are complete; nobody else reads them
+        // ---- GEMM B, this warp's 16 neurons: pb[qt][ct] = sum_n G[8 qt + g][n] CC[8 ct + 2 tg + e][n]
+        if (need_lat) {
+            double pb[2][NC][2];
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt)
+#pragma unroll
+                for (int ct = 0; ct < NC; ++ct) pb[qt][ct][0] = pb[qt][ct][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int n = 16 * warp + 4 * ks + tg;
+                double ga[2];
+#pragma unroll
+                for (int qt = 0; qt < 2; ++qt) ga[qt] = Gs[(8 * qt + g) * TNS + n];
+#pragma unroll
+                for (int ct = 0; ct < NC; ++ct) {
+                    const double b = CC[(8 * ct + g) * TNS + n];
+#pragma unroll
+                    for (int qt = 0; qt < 2; ++qt) dmma(pb[qt][ct][0], pb[qt][ct][1], ga[qt], b);
+                }
+            }
+            // the eight partial results meet in shared memory, in fragment layout (one conflict-free 16-byte store per tile)
+            double* mine = redB + (size_t)warp * NTB * 64 + 2 * lane;
+#pragma unroll
+            for (int qt = 0; qt < 2; ++qt)
+#pragma unroll
+                for (int ct = 0; ct < NC; ++ct)
+                    *reinterpret_cast<double2*>(mine + (qt * NC + ct) * 64) = make_double2(pb[qt][ct][0], pb[qt][ct][1]);
+            // ---- GEMM C in between (independent of the exchange): accumulate G^T [Mu | Var] over the 16 points
+            if (need_emb) {
+#pragma unroll
+                for (int ks = 0; ks < EMM_TQ / 4; ++ks) {
+                    double ga[2];
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) ga[nl] = Gs[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+#pragma unroll
+                    for (int ct = 0; ct < NC; ++ct) {
+                        const double b = stT[(8 * ct + g) * LDQ + 4 * ks + tg];
+#pragma unroll
+                        for (int nl = 0; nl < 2; ++nl) dmma(cc[nl][ct][0], cc[nl][ct][1], ga[nl], b);
+                    }
+                }
+            }
+            __syncthreads();                      // everyone is done with stT; all partials are in place
+            // 8 -> 1 and out: thread <-> (tile, fragment lane); rows of 8 consecutive points per (column, g-run)
+            for (int u = tid; u < NTB * 32; u += EMM_THREADS) {
+                const double2* p = reinterpret_cast<const double2*>(redB + 2 * u);
+                double2 s = p[0];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) {
+                    const double2 x = p[w * NTB * 32];
+                    s.x += x.x;
+                    s.y += x.y;
+                }
+                const int tl = u >> 5, ln = u & 31, qt = tl / NC, ct = tl - qt * NC;
+                const int q = q0 + 8 * qt + (ln >> 2), c = 8 * ct + 2 * (ln & 3);
+                if (q < Q) {
+                    if (c < K) bf.mubar_part[part_off + ((size_t)r * K + c) * Q + q] = s.x;
+                    else if (c < K2) bf.varbar_part[part_off + ((size_t)r * K + c - K) * Q + q] = s.x;
+                    if (c + 1 < K) bf.mubar_part[part_off + ((size_t)r * K + c + 1) * Q + q] = s.y;
+                    else if (c + 1 < K2) bf.varbar_part[part_off + ((size_t)r * K + c + 1 - K) * Q + q] = s.y;
+                }
+            }
+        } else {
+            if (need_emb) {
+#pragma unroll
+                for (int ks = 0; ks < EMM_TQ / 4; ++ks) {
+                    double ga[2];
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) ga[nl] = Gs[(4 * ks + tg) * TNS + 8 * (2 * warp + nl) + g];
+#pragma unroll
+                    for (int ct = 0; ct < NC; ++ct) {
+                        const double b = stT[(8 * ct + g) * LDQ + 4 * ks + tg];
+#pragma unroll
+                        for (int nl = 0; nl < 2; ++nl) dmma(cc[nl][ct][0], cc[nl][ct][1], ga[nl], b);
+                    }
+                }
+            }
+            __syncthreads();                      // everyone is done with stT
+        }
+    }
+    // ---- flush: dC[n][k] = (G^T Mu)[n][k] + C[n][k] (G^T Var)[n][k];  dd[n] = sum_q G[q][n]
+    if (need_emb) {
+        double* gC = bf.shared + SVGPFA_SHARED_HDR;
+        double* gd = gC + (size_t)N * K;
+#pragma unroll
+        for (int nl = 0; nl < 2; ++nl) {
+            const int nn = 8 * (2 * warp + nl) + g, n = n0 + nn;
+            if (n < N) {
+#pragma unroll
+                for (int ct = 0; ct < NC; ++ct)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * ct + 2 * tg + e;
+                        if (c < K) atomicAdd(gC + (size_t)n * K + c, cc[nl][ct][e]);
+                        else if (c < K2) atomicAdd(gC + (size_t)n * K + c - K, CC[(c - K) * TNS + nn] * cc[nl][ct][e]);
+                    }
+            }
+            // dsum[nl][e]: this lane's points of neuron 8 (2 warp + nl) + 2 tg + e; the other points sit in the lanes g' != g
+            double s0 = dsum[nl][0], s1 = dsum[nl][1];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            const int nd = n0 + 8 * (2 * warp + nl) + 2 * tg;
+            if (g == 0) {
+                if (nd < N) atomicAdd(gd + nd, s0);
+                if (nd + 1 < N) atomicAdd(gd + nd + 1, s1);
+            }
+        }
+    }
+    const double tot = block_sum(t1, red);
+    if (tid == 0) {
+        const int slot = (blockIdx.y * gridDim.x + blockIdx.x) % SVGPFA_TERM1_SLOTS;
+        atomicAdd(bf.term1_part + slot, tot);
+    }
+}
+
+template <int NC>
+void launch_emc(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    const size_t smem = sizeof(double) * emc_smem_doubles(NC);
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = occ_cache[dev & 63].load(std::memory_order_relaxed);
+    if (occ <= 0) {
+        cudaFuncSetAttribute(quad_embed_cat_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(quad_embed_cat_kernel<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quad_embed_cat_kernel<NC>, EMM_THREADS, smem);
+        if (occ < 1) occ = 1;
+        occ_cache[dev & 63].store(occ, std::memory_order_relaxed);
+    }
+    const int ntiles = (dims->N + EMM_TN - 1) / EMM_TN;
+    const int qtiles = (dims->Q + EMM_TQ - 1) / EMM_TQ;
+    const long nitems = (long)svgpfa_ntrials(dims) * qtiles;
+    long workers = (long)svgpfa_sm_count() * occ / ntiles;
+    if (workers < 1) workers = 1;
+    if (workers > nitems) workers = nitems;
+    quad_embed_cat_kernel<NC><<<dim3(ntiles, (unsigned)workers), EMM_THREADS, smem, st>>>(*dims, *buf, flags);
+}
+
 template <int KT>
 void launch_emm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
     // shared memory depends on KP = 8 KT only, so the attribute and the occupancy are fixed per instantiation
@@ -849,6 +1110,15 @@ void launch_emm(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t fla
 
 // Returns false when K is outside this path (K + 1 > 40 latents); the caller then uses the CUDA-core kernel.
 bool svgpfa_try_quad_embed_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, cudaStream_t st) {
+    switch ((2 * dims->K + 7) / 8) {                  // K <= 24: the concatenated-statistics kernel
+        case 1: launch_emc<1>(dims, buf, flags, st); return true;
+        case 2: launch_emc<2>(dims, buf, flags, st); return true;
+        case 3: launch_emc<3>(dims, buf, flags, st); return true;
+        case 4: launch_emc<4>(dims, buf, flags, st); return true;
+        case 5: launch_emc<5>(dims, buf, flags, st); return true;
+        case 6: launch_emc<6>(dims, buf, flags, st); return true;
+        default: break;
+    }
     const int KT = emm_kp(dims->K) / 8;
     switch (KT) {
         case 1: launch_emm<1>(dims, buf, flags, st); break;
