@@ -94,6 +94,36 @@ def test_inducing_point_counts_up_to_64(M_list, Q):
     assert worst[0] <= GRAD_TOL, worst
 
 
+@pytest.mark.parametrize("K,N,Q", [(1, 5, 16), (5, 130, 20), (13, 9, 33), (16, 257, 16), (21, 40, 17), (24, 7, 16), (26, 12, 16), (39, 6, 8)])
+def test_latent_counts_cover_every_embedding_kernel_shape(K, N, Q):
+    """The embedding / exp-link / integral stage for every class of K: the concatenated-statistics kernel with
+    ceil(2K / 8) = 1 .. 6 column tiles (K <= 24; table exp up to 4 tiles, libdevice above), the separate-statistics kernel
+    (K = 25 .. 39), neuron counts around the 128-neuron tile, Q not a multiple of the 16-point item -- against the oracle
+    executed on the box."""
+    from oracle import svgpfa_oracle as orc
+    cfg = dict(R=3, N=N, K=K, M=4, Q=Q, mixed=True, ragged=False)
+    case = synthetic.make_case(cfg, seed=5, reg=1e-3)
+    ref = orc.elbo_and_grads(case)
+    _, out = _eval_all(case)
+    assert abs(out["elbo"] - ref["elbo"]) <= ELBO_TOL * abs(ref["elbo"])
+    worst = max((rel_err(out[key], ref[key]), key) for key in _grad_keys(K))
+    assert worst[0] <= GRAD_TOL, worst
+    # the closure of an E-step: posterior gradients only (no GEMM C in the embedding stage, V cache reused)
+    from svgpfa_b200.testing import model_from_case, set_requires_grad, grads_as_dict
+    model = model_from_case(case)
+    set_requires_grad(model, posterior=True, embedding=False, kernels=False, indlocs=False)
+    for _ in range(2):
+        for p in model.getSVPosteriorOnIndPointsParams():
+            p.grad = None
+        v = model.eval()
+        v.backward()
+        got = grads_as_dict(model)
+        assert abs(v.item() - ref["elbo"]) <= ELBO_TOL * abs(ref["elbo"])
+        for k in range(K):
+            assert rel_err(got[f"grad_m_{k}"], ref[f"grad_m_{k}"]) <= GRAD_TOL
+            assert rel_err(got[f"grad_chol_vecs_{k}"], ref[f"grad_chol_vecs_{k}"]) <= GRAD_TOL
+
+
 @pytest.mark.parametrize("M,mixed", [(32, False), (20, True), (16, False)])
 def test_spike_tiles_and_segments_across_tile_boundaries(M, mixed):
     """The spike kernel stages 1024 spike times per shared-memory tile.  With the neuron range of a CTA forced to the
