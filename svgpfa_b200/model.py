@@ -486,7 +486,9 @@ class B200SVLowerBound:
         if use and self.spike_method == "auto":
             NB, KM, Kp = B * _cabi.PM_P, self._KM, 8 * ((self._K + 7) // 8)
             panel_cost = self._R * NB * (30.0 * KM + 2.0 * self._N * Kp + 45.0 * self._N)
-            direct_cost = 13.0 * self._S * KM
+            # the direct kernel gives a lane to every (latent, inducing point) pair of a trial, 128 pairs per CTA: with
+            # few pairs (config #2: 27) most lanes idle, and its cost is that of the padded pair count
+            direct_cost = 13.0 * self._S * 128.0 * math.ceil(KM / 128.0)
             tau_bytes = 8.0 * self._R * self._N * NB
             use = (1.5 * panel_cost < direct_cost and self._K <= 40 and self._N <= 8000
                    and tau_bytes <= 0.3 * torch.cuda.get_device_properties(dev).total_memory)
