@@ -9,7 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "svgpfa_b200", "libsvgpfa_b200.so")
-WANT = ("quad_latent_mma_kernelILi4ELb1", "quad_latent_mma_kernelILi4ELb0", "quad_embed_mma_kernelILi3",
+WANT = ("quad_latent_mma_kernelILi4ELb1ELi1", "quad_latent_mma_kernelILi4ELb0ELi1", "quad_latent_mma_kernelILi4ELb0ELi2",
+        "quad_embed_cat_kernelILi5", "quad_embed_mma_kernelILi4",
         "indpoints_bwd_mma_kernelILi4", "panel_weights_kernelILi3ELi2", "panel_dC_kernelILi3", "panel_adjoint_kernelILb1",
         "panel_nodal_means_kernel", "panel_moments_kernelILi1", "kzz_chol_warp_kernelILb1", "indpoints_fwd_warp_kernel",
         "spike_tile_kernelILb1", "spike_gather_kernel", "lb_multidot_kernelILi3", "lb_combine_kernelILb0", "lb_update_kernel",
