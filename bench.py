@@ -574,7 +574,11 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "b200",
             "config": config_dict(args, cfg, world), "elbo": elbo, "shared_checksum": checksum,
             "spikes_total": int(tot_S.item()), "trial_blocks": [list(b) for b in blocks],
-            "clocks": clocks, "gpu_launches": 10 * args.steps, "closures": closures,
+            # library kernels per evaluation inside the timed region (profiles/r02_launches_config5_1gpu.csv): Cholesky
+            # (+ inducing-point forward, one launch for M <= 32), quadrature forward, embedding, quadrature adjoint, the
+            # spike-time term (4 panel kernels or the direct kernel), inducing-point adjoint, two finalize kernels
+            "clocks": clocks, "gpu_launches": ((1 if cfg["M"] <= 32 else 2) + 3 + (4 if panel else 1) + 1 + 2) * args.steps,
+            "closures": closures,
             "stages_ms": {n: float(x) for n, x in zip(_cabi.STAGES, st.tolist())},
             "roofline": roofline, "peaks_measured": {k: float(v) for k, v in peaks.items()}}
     if e2e is not None:
