@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libsvgpfa_b200.so")
-SOURCES = ["api.cu", "indpoints.cu", "quad.cu", "quad_mma.cu", "spike.cu", "panel.cu", "lbfgs.cu"]
+SOURCES = ["api.cu", "indpoints.cu", "quad.cu", "quad_mma.cu", "quad_mma64.cu", "spike.cu", "panel.cu", "lbfgs.cu"]
 # measurement probes and test hooks: a separate library, never loaded by the product path
 PROBES_LIB = os.path.join(PKG, "libsvgpfa_b200_probes.so")
 PROBES_SOURCES = ["probes.cu"]

@@ -7,6 +7,7 @@
 //  stats/svEmbedding.py:80-84, stats/expectedLogLikelihood.py:107-135,205-208).
 #include "common.cuh"
 
+bool svgpfa_try_quad_latent_big(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd, cudaStream_t st);
 bool svgpfa_try_quad_latent_mma(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, bool bwd,
                                 cudaStream_t st);
 
@@ -613,7 +614,8 @@ extern "C" int svgpfa_embed_predict(const svgpfa_dims* dims, const svgpfa_buffer
 extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
-    if (use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, 0, false, (cudaStream_t)stream)) {
+    if (use_mma_path() && (svgpfa_try_quad_latent_mma(dims, buf, 0, false, (cudaStream_t)stream) ||
+                           svgpfa_try_quad_latent_big(dims, buf, 0, false, (cudaStream_t)stream))) {
         SVGPFA_CHECK_LAUNCH("quad_latent_fwd (mma)");
         return SVGPFA_OK;
     }
@@ -628,7 +630,8 @@ extern "C" int svgpfa_quad_latent_fwd(const svgpfa_dims* dims, const svgpfa_buff
 extern "C" int svgpfa_quad_latent_fwd_cached(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_fwd_cached", cudaSuccess);
     if (dims->R == 0 || dims->Q == 0) return SVGPFA_OK;
-    if (buf->v_q && use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, SVGPFA_REUSE_VQ, false, (cudaStream_t)stream)) {
+    if (buf->v_q && use_mma_path() && (svgpfa_try_quad_latent_mma(dims, buf, SVGPFA_REUSE_VQ, false, (cudaStream_t)stream) ||
+                                       svgpfa_try_quad_latent_big(dims, buf, SVGPFA_REUSE_VQ, false, (cudaStream_t)stream))) {
         SVGPFA_CHECK_LAUNCH("quad_latent_fwd_cached (mma)");
         return SVGPFA_OK;
     }
@@ -638,7 +641,8 @@ extern "C" int svgpfa_quad_latent_fwd_cached(const svgpfa_dims* dims, const svgp
 extern "C" int svgpfa_quad_latent_bwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, uint32_t flags, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M) return svgpfa_set_error(SVGPFA_E_ARG, "quad_latent_bwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    if (use_mma_path() && svgpfa_try_quad_latent_mma(dims, buf, flags, true, (cudaStream_t)stream)) {
+    if (use_mma_path() && (svgpfa_try_quad_latent_mma(dims, buf, flags, true, (cudaStream_t)stream) ||
+                           svgpfa_try_quad_latent_big(dims, buf, flags, true, (cudaStream_t)stream))) {
         SVGPFA_CHECK_LAUNCH("quad_latent_bwd (mma)");
         return SVGPFA_OK;
     }

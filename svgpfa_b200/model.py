@@ -404,7 +404,7 @@ class B200SVLowerBound:
         # V = L^-1 kappa(Z, t_q) of every quadrature point, handed from the forward to the adjoint quadrature kernel
         # (include/svgpfa_b200.h: buffers.v_q) when it fits comfortably: 20.5 GB at config #5
         vq_bytes = 8 * R * self._KM * Q
-        if getattr(self, "v_cache", True) and max(self._M) <= 32 and Q % 2 == 0 and vq_bytes > 0:
+        if getattr(self, "v_cache", True) and max(self._M) <= 64 and Q % 2 == 0 and vq_bytes > 0:
             free, _ = torch.cuda.mem_get_info(dev)
             if vq_bytes <= 0.4 * free:
                 ws["v_q"] = e(R * self._KM * Q)
