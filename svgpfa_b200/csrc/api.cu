@@ -389,7 +389,16 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
     // the next block's (20000 trials: 274.0 -> 269.6 ms, 2500 trials: 36.3 -> 35.4 ms).  Both streams accumulate into `shared` with atomics; per-trial outputs never overlap.
     const bool two = hp != nullptr;
     if (two) cudaStreamWaitEvent(hp->comp2, hp->start, 0);
-    auto r_of = [&](int b) { return (size_t)(R * (size_t)b / (size_t)nb); };
+    // Block boundaries.  The copy-in of the first block and the copy-out of the last one cannot hide under kernels, so
+    // the blocks at both ends are small and grow towards the middle: weights 1, 2, 3, 4, 4, ..., 4, 3, 2, 1.
+    size_t bw_prefix[HP_MAX_BLOCKS + 1];
+    bw_prefix[0] = 0;
+    for (int b = 0; b < nb; ++b) {
+        int w = b + 1 < nb - b ? b + 1 : nb - b;
+        if (w > 4) w = 4;
+        bw_prefix[b + 1] = bw_prefix[b] + (size_t)w;
+    }
+    auto r_of = [&](int b) { return (size_t)(R * bw_prefix[b] / bw_prefix[nb]); };
     // K-major arrays: the block's trials are K separate runs, one per latent; with a uniform M they form a 2-D copy
     bool uniform = true;
     for (int k = 1; k < dims->K; ++k) uniform = uniform && dims->desc_host[k].M == dims->desc_host[0].M;
