@@ -390,12 +390,12 @@ extern "C" int svgpfa_elbo_grad_host(const svgpfa_dims* dims, const svgpfa_buffe
     const bool two = hp != nullptr;
     if (two) cudaStreamWaitEvent(hp->comp2, hp->start, 0);
     // Block boundaries.  The copy-in of the first block and the copy-out of the last one cannot hide under kernels, so
-    // the blocks at both ends are small and grow towards the middle: weights 1, 2, 3, 4, 4, ..., 4, 3, 2, 1.
+    // the blocks at both ends are small and grow towards the middle: weights 1, 2, ..., 8, 8, ..., 2, 1.
     size_t bw_prefix[HP_MAX_BLOCKS + 1];
     bw_prefix[0] = 0;
     for (int b = 0; b < nb; ++b) {
         int w = b + 1 < nb - b ? b + 1 : nb - b;
-        if (w > 4) w = 4;
+        if (w > 8) w = 8;
         bw_prefix[b + 1] = bw_prefix[b] + (size_t)w;
     }
     auto r_of = [&](int b) { return (size_t)(R * bw_prefix[b] / bw_prefix[nb]); };

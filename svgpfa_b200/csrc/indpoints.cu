@@ -1,7 +1,8 @@
-// Batched per-(trial, latent) M x M work, M <= 64, one CTA per matrix, everything staged in
-// shared memory:
-//   kzz_chol_kernel       Kzz = kappa(Z,Z)+reg I, L = chol(Kzz), Li = L^-1, sum log L_ii
-//   indpoints_fwd_kernel  Ls, X = Li Ls, c = Li m, alpha = Li^T c, KL_rk
+// Batched per-(trial, latent) M x M work, M <= 64:
+//   kzz_chol_warp_kernel (M <= 32, warp per matrix), kzz_chol_pair_kernel (M <= 64, two warps per matrix)
+//                         Kzz = kappa(Z,Z)+reg I, L = chol(Kzz), Li = L^-1, sum log L_ii; fused with the stage below
+//                         inside svgpfa_elbo_grad
+//   indpoints_fwd_warp_kernel (M <= 32), indpoints_fwd_kernel      Ls, X = Li Ls, c = Li m, alpha = Li^T c, KL_rk
 //   indpoints_bwd_mma_kernel  adjoints through alpha, c, X, KL and the Cholesky factorisation (M <= 64)
 // Reference arithmetic: stats/kernelsMatricesStore.py:107-138, utils/miscUtils.py:135-155,209-216,
 // stats/klDivergence.py:31-44; adjoints per SURVEY.md Appendix A (the reference uses autograd).
@@ -14,77 +15,9 @@ constexpr int IP_THREADS = 128;
 __device__ __forceinline__ int ld_of(int M) { return M | 1; }   // odd leading dimension: conflict-free columns
 
 // ------------------------------------------------------------------------------------------
-// ONEWARP (M <= 32): the CTA is a single warp and every barrier is a __syncwarp.
-template <bool ONEWARP>
-__global__ void __launch_bounds__(64) kzz_chol_kernel(svgpfa_dims dm, svgpfa_buffers bf) {
-    auto sync = [] { if (ONEWARP) __syncwarp(); else __syncthreads(); };
-    extern __shared__ double sm[];
-    const int r = dm.r0 + blockIdx.x, k = blockIdx.y;
-    const svgpfa_latent_desc ds = bf.desc[k];
-    const int M = ds.M, ld = ld_of(M);
-    double* A = sm;                 // M x ld : Kzz -> L
-    double* B = A + M * ld;         // M x ld : Li
-    double* zs = B + M * ld;        // M
-    double* dinv = zs + M;          // M
-    const int tid = threadIdx.x, T = blockDim.x;
-    const KConst kc = make_kconst(ds, bf.theta, bf.kscale, k);
-    const double* z = bf.Z + (size_t)dm.R * ds.moff + (size_t)r * M;
-    for (int i = tid; i < M; i += T) zs[i] = z[i];
-    sync();
-    for (int idx = tid; idx < M * M; idx += T) {
-        const int i = idx / M, j = idx - i * M;
-        if (j <= i) A[i * ld + j] = kappa_val(kc, zs[i] - zs[j]) + (i == j ? dm.reg : 0.0);
-    }
-    sync();
-    // left-looking Cholesky, thread i owns row i
-    bool bad = false;
-    for (int j = 0; j < M; ++j) {
-        double s = 0.0;
-        if (tid >= j && tid < M) {
-            s = A[tid * ld + j];
-            for (int p = 0; p < j; ++p) s -= A[tid * ld + p] * A[j * ld + p];
-        }
-        if (tid == j) {
-            if (!(s > 0.0)) bad = true;
-            const double dg = sqrt(s);
-            A[j * ld + j] = dg;
-            dinv[j] = 1.0 / dg;
-        }
-        sync();
-        if (tid > j && tid < M) A[tid * ld + j] = s * dinv[j];
-        sync();
-    }
-    if (bad) {
-        if (atomicCAS(bf.info, 0, SVGPFA_INFO_NOT_PD) == 0) { bf.info[1] = r; bf.info[2] = k; }
-    }
-    // Li by forward substitution, thread c owns column c
-    if (tid < M) {
-        const int c = tid;
-        for (int i = 0; i < M; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int p = c; p < i; ++p) s -= A[i * ld + p] * B[p * ld + c];
-            B[i * ld + c] = (i < c) ? 0.0 : s * dinv[i];
-        }
-    }
-    sync();
-    double* Lg = bf.L + (size_t)r * dm.MM + ds.mmoff;
-    double* Lig = bf.Li + (size_t)r * dm.MM + ds.mmoff;
-    for (int idx = tid; idx < M * M; idx += T) {
-        const int i = idx / M, j = idx - i * M;
-        Lg[idx] = (j <= i) ? A[i * ld + j] : 0.0;
-        Lig[idx] = (j <= i) ? B[i * ld + j] : 0.0;
-    }
-    if (tid == 0) {
-        double s = 0.0;
-        for (int i = 0; i < M; ++i) s += log(A[i * ld + i]);
-        bf.logdetL[(size_t)r * dm.K + k] = s;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // M <= 32: one WARP per (trial, latent) matrix, rows in registers.
-// The kernel above keeps the matrix in shared memory (two loads per FMA, one thread per row or column) and needed
-// ~110 k cycles per matrix (ncu: 45 % fixed-latency "wait" stalls, 36 % of the samples in the column-wise inverse).
+// The first version (one thread per row or column, the matrix in shared memory: two loads per FMA) needed ~110 k cycles
+// per matrix (ncu: 45 % fixed-latency "wait" stalls, 36 % of the samples in the column-wise inverse).
 // Here lane i owns ROW i of the trailing matrix in registers: a right-looking Cholesky whose column broadcasts are warp
 // shuffles, written with a rotating register window (after column j is eliminated a[k-1] <- a[k] - l_ij l_kj, so the
 // loop over j stays rolled and the code small), followed by the column-wise inverse with lane c owning column c of
@@ -334,9 +267,9 @@ __global__ void __launch_bounds__(32 * KC_WARPS) indpoints_fwd_warp_kernel(svgpf
 // version passes through shuffles goes through shared memory here: every thread posts its entry of the current
 // column UNNORMALISED, one barrier, and everybody reads the pivot d and the column from there,
 //     a[k-1] <- a[k] - (a_i / d) a_k        (= a[k] - l_ij l_kj),
-// so a column costs one barrier (the column buffer is double-buffered).  Replaces the one-thread-per-row kernel
-// above, which read both factors of every product from shared memory (M = 64, R = 1000: 4.7 + 1.9 ms for the
-// Cholesky and the inducing-point forward stage).
+// so a column costs one barrier (the column buffer is double-buffered).  Replaces a one-thread-per-row kernel that
+// read both factors of every product from shared memory (M = 64, R = 1000: 4.7 + 1.9 ms for the Cholesky and the
+// inducing-point forward stage, 2.7 ms now).
 constexpr int KP_N = 64, KP_LD = 65, KP_COL = 128;
 
 template <int LEN>
@@ -762,13 +695,11 @@ size_t ip_smem(int Mmax, int nmat, int nvec) {
 extern "C" int svgpfa_kzz_chol_fwd(const svgpfa_dims* dims, const svgpfa_buffers* buf, void* stream) {
     if (!dims || !buf || dims->Mmax > SVGPFA_MAX_M || dims->Mmax < 1) return svgpfa_set_error(SVGPFA_E_ARG, "kzz_chol_fwd", cudaSuccess);
     if (dims->R == 0) return SVGPFA_OK;
-    const size_t smem = ip_smem(dims->Mmax, 2, 2);
     if (dims->Mmax <= 32) {
         const int nprob = svgpfa_ntrials(dims) * dims->K;
         const size_t wsm = sizeof(double) * KC_WARPS * KC_WSM;
         kzz_chol_warp_kernel<false><<<(nprob + KC_WARPS - 1) / KC_WARPS, 32 * KC_WARPS, wsm, (cudaStream_t)stream>>>(*dims, *buf, nprob);
     } else {
-        (void)smem;
         kzz_chol_pair_kernel<false><<<dim3(svgpfa_ntrials(dims), dims->K), KP_N, 0, (cudaStream_t)stream>>>(*dims, *buf);
     }
     SVGPFA_CHECK_LAUNCH("kzz_chol_fwd");
