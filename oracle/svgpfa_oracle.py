@@ -212,6 +212,15 @@ def kl_divergence(Kzz, Lzz, m, covs):
 # --------------------------------------------------------------------------------------
 # the whole path
 # --------------------------------------------------------------------------------------
+def build_covs_rank1(q_svec, q_sdiag):
+    """S_kr = q q^T + diag(d^2): the rank-1-plus-diagonal parameterisation
+    (svPosteriorOnIndPoints.py:86-119, SVPosteriorOnIndPointsRank1PlusDiag.buildCov)."""
+    covs = []
+    for q, d in zip(q_svec, q_sdiag):
+        covs.append(q @ q.transpose(1, 2) + torch.diag_embed(d[:, :, 0] ** 2))
+    return covs
+
+
 def to_tensors(case, requires_grad=False):
     t = lambda a: torch.tensor(np.asarray(a), dtype=F64)
     p = dict(m=[t(a) for a in case["m"]], chol_vecs=[t(a) for a in case["chol_vecs"]],
@@ -248,7 +257,7 @@ def elbo_terms(case, p, spike_var=True):
     Kzz, Lzz = build_kzz(kt, p["kernel_params"], p["Z"], reg)
     Ktz_q, ktt_q = build_ktz_quad(kt, p["kernel_params"], p["Z"], tq)
     Ktz_s, ktt_s = build_ktz_spikes(kt, p["kernel_params"], p["Z"], times)
-    covs = build_covs(p["chol_vecs"])
+    covs = build_covs_rank1(p["q_svec"], p["q_sdiag"]) if "q_svec" in p else build_covs(p["chol_vecs"])
     mu_q, var_q = latents_at_quad(Kzz, Lzz, Ktz_q, ktt_q, p["m"], covs)
     mu_s, var_s = latents_at_spikes(Kzz, Lzz, Ktz_s, ktt_s, p["m"], covs, with_var=spike_var)
     eq_mu, eq_var = embed_quad(mu_q, var_q, p["C"], p["d"])
@@ -294,3 +303,24 @@ def ell_from_cached_stats(case, mu_q, var_q, mu_s, C, d):
     eq_mu, eq_var = embed_quad(mu_q, var_q, C, d)
     es_mu, _ = embed_spikes(mu_s, [None] * len(mu_s), C, d, idx)
     return ell_exp_link(eq_mu, eq_var, es_mu, w)
+
+
+def elbo_and_grads_rank1(case, q_svec, q_sdiag):
+    """The same unit of work with the variational covariance given as (q, d) instead of Cholesky vectors
+    (stats/svGPFAModelFactory.py: indPointsCovRep = indPointsCovRank1PlusDiag)."""
+    p = to_tensors(case, requires_grad=True)
+    p.pop("chol_vecs")
+    p["q_svec"] = [torch.tensor(np.asarray(a), dtype=F64, requires_grad=True) for a in q_svec]
+    p["q_sdiag"] = [torch.tensor(np.asarray(a), dtype=F64, requires_grad=True) for a in q_sdiag]
+    ell, kl, _ = elbo_terms(case, p, spike_var=False)
+    elbo = ell - kl
+    elbo.backward()
+    out = {"elbo": elbo.item(), "ell": ell.item(), "kl": kl.item(),
+           "grad_C": p["C"].grad.numpy(), "grad_d": p["d"].grad.numpy()}
+    for k in range(len(case["kernel_types"])):
+        out[f"grad_m_{k}"] = p["m"][k].grad.numpy()
+        out[f"grad_q_svec_{k}"] = p["q_svec"][k].grad.numpy()
+        out[f"grad_q_sdiag_{k}"] = p["q_sdiag"][k].grad.numpy()
+        out[f"grad_kernel_params_{k}"] = p["kernel_params"][k].grad.numpy()
+        out[f"grad_Z_{k}"] = p["Z"][k].grad.numpy()
+    return out

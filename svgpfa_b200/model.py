@@ -155,7 +155,17 @@ class B200SVLowerBound:
     _PENDING_SLOTS = 8
     _stats_serial = 0
 
-    def __init__(self, kernels=None, device=None, process_group=None, check_errors=True, shard_mode="auto"):
+    def __init__(self, kernels=None, device=None, process_group=None, check_errors=True, shard_mode="auto",
+                 ind_points_cov_rep="chol"):
+        if ind_points_cov_rep not in ("chol", "rank1_plus_diag"):
+            raise ValueError("ind_points_cov_rep must be 'chol' or 'rank1_plus_diag'")
+        # how the variational covariance S_kr is parameterised (stats/svGPFAModelFactory.py:29-32):
+        #   "chol"             Cholesky vectors, S = Ls Ls^T          (SVPosteriorOnIndPointsChol, the default)
+        #   "rank1_plus_diag"  S = q q^T + diag(d^2)                  (SVPosteriorOnIndPointsRank1PlusDiag)
+        # The kernels consume Cholesky vectors; with (q, d) they are DERIVED on the device at every evaluation
+        # (batched torch.linalg.cholesky of q q^T + diag(d^2): plumbing, O(R K M^3) against the path's O(R K Q M^2))
+        # and the gradient the kernels return for them is carried on to (q, d) by autograd.
+        self._cov_rep = ind_points_cov_rep
         self._device = torch.device(device) if device is not None else None
         self._pg = process_group
         if shard_mode not in ("auto", "reduce", "local"):
@@ -238,7 +248,29 @@ class B200SVLowerBound:
         self._m = [self._mbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
         self._cv = [self._cvbuf[R * self._poff[k]:R * self._poff[k + 1]].view(R, self._P[k], 1) for k in range(K)]
         self._theta = [self._thbuf[self._thoff[k]:self._thoff[k + 1]] for k in range(K)]
+        if getattr(self, "_cov_rep", "chol") == "rank1_plus_diag":
+            self._qv = [self._qvbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
+            self._qd = [self._qdbuf[R * self._moff[k]:R * self._moff[k + 1]].view(R, self._M[k], 1) for k in range(K)]
         self._leaf_list = None
+
+    def _rank1(self):
+        return getattr(self, "_cov_rep", "chol") == "rank1_plus_diag"
+
+    def _derive_cholvecs(self):
+        """Rank-1-plus-diagonal parameterisation: Cholesky vectors of S = q q^T + diag(d^2) (row-major tril order,
+        miscUtils.py:135-139) as tensors ATTACHED to the autograd graph of (q, d); their values are also written
+        into the packed buffer the kernels read (svPosteriorOnIndPoints.py:103-115, buildCov)."""
+        out = []
+        for k in range(self._K):
+            q, dg = self._qv[k][:, :, 0], self._qd[k][:, :, 0]
+            S = q.unsqueeze(2) * q.unsqueeze(1) + torch.diag_embed(dg * dg)
+            L = torch.linalg.cholesky(S)
+            ti = torch.tril_indices(self._M[k], self._M[k], device=L.device)
+            cv = L[:, ti[0], ti[1]].unsqueeze(-1)
+            with torch.no_grad():
+                self._cv[k].copy_(cv)
+            out.append(cv)
+        return out
 
     def _refresh_leaf_list(self):
         self._leaf_list = list(self._m) + list(self._cv) + [self._C, self._d] + list(self._theta) + list(self._Z)
@@ -251,7 +283,12 @@ class B200SVLowerBound:
             raise RuntimeError("setKernels must be called before setInitialParams")
         pol = initial_params["posterior_on_latents"]
         mean = pol["posterior_on_ind_points"]["mean"]
-        chol = pol["posterior_on_ind_points"]["cholVecs"]
+        if self._rank1():
+            # (R, M, 1) each (svPosteriorOnIndPoints.py:91-94); the Cholesky vectors are derived, see _derive_cholvecs
+            qsv, qsd = pol["posterior_on_ind_points"]["qSVec0"], pol["posterior_on_ind_points"]["qSDiag0"]
+            chol = [torch.zeros(int(q.shape[0]), _tril_size(int(q.shape[1])), 1, dtype=_F64) for q in qsv]
+        else:
+            chol = pol["posterior_on_ind_points"]["cholVecs"]
         kms = pol["kernels_matrices_store"]
         theta0, Z0 = kms["kernels_params0"], kms["inducing_points_locs0"]
         C0, d0 = initial_params["embedding"]["C0"], initial_params["embedding"]["d0"]
@@ -279,6 +316,11 @@ class B200SVLowerBound:
         self._KM, self._PP, self._TH, self._MM = self._moff[-1], self._poff[-1], self._thoff[-1], self._mmoff[-1]
         pack = lambda xs: torch.cat([self._to_dev(x).reshape(-1) for x in xs]).contiguous()
         self._Zbuf, self._mbuf, self._cvbuf, self._thbuf = pack(Z0), pack(mean), pack(chol), pack(theta0)
+        if self._rank1():
+            for k in range(K):
+                if tuple(qsv[k].shape) != (R, self._M[k], 1) or tuple(qsd[k].shape) != (R, self._M[k], 1):
+                    raise ValueError(f"latent {k}: expected qSVec0 and qSDiag0 of shape (R,M,1)")
+            self._qvbuf, self._qdbuf = pack(qsv), pack(qsd)
         self._make_views()
         self._C = self._to_dev(C0).contiguous().clone()
         self._d = self._to_dev(d0).contiguous().clone()
@@ -290,6 +332,9 @@ class B200SVLowerBound:
         self._params_set = True
         self._ready = False
         self._kzz_key = self._spike_key = self._vq_key = None
+        if self._rank1():
+            with torch.no_grad():
+                self._derive_cholvecs()
 
     def setMeasurements(self, measurements):
         """``measurements[r][n]`` = spike times of neuron n in trial r (list / array / tensor, float32
@@ -356,6 +401,8 @@ class B200SVLowerBound:
 
     # ------------------------------------------------------------------ getters (svLowerBound.py:101-114)
     def getSVPosteriorOnIndPointsParams(self):
+        if self._rank1():                  # mean, qSVec, qSDiag (svPosteriorOnIndPoints.py:96-101)
+            return list(self._m) + list(self._qv) + list(self._qd)
         return list(self._m) + list(self._cv)
 
     def getSVEmbeddingParams(self):
@@ -372,6 +419,14 @@ class B200SVLowerBound:
 
     # ------------------------------------------------------------------ buffers
     def _prepare(self):
+        if self._rank1() and self._params_set:
+            # the packed Cholesky vectors follow (q, d) for the entries that do not go through _apply (latent statistics,
+            # read-outs)
+            key = (self._qvbuf._version, self._qdbuf._version)
+            if getattr(self, "_cov_key", None) != key:
+                with torch.no_grad():
+                    self._derive_cholvecs()
+                self._cov_key = key
         if self._ready:
             return
         if not (self._params_set and self._spikes_set and self._quad_set and self._reg is not None):
@@ -614,6 +669,9 @@ class B200SVLowerBound:
     def _apply(self, cached_stats):
         self._poll_errors(block=False)
         leaves = self._leaf_list
+        if self._rank1():                  # the Cholesky-vector slots carry tensors derived from (q, d)
+            K = self._K
+            leaves = leaves[:K] + self._derive_cholvecs() + leaves[2 * K:]
         differentiated = torch.is_grad_enabled() and any(p.requires_grad for p in leaves)
         out = _LowerBoundFn.apply(self, cached_stats, *leaves)
         if not differentiated:
@@ -643,9 +701,12 @@ class B200SVLowerBound:
                     info=z(4, torch.int32))
 
     def evalAndGradHost(self, io, flags=_cabi.GRAD_ALL, copy_static=True, n_blocks=0):
-        """One unit of work through the C ABI with HOST buffers: host->device copies of the inputs,
+        """(Cholesky-vector parameterisation only.)
+        One unit of work through the C ABI with HOST buffers: host->device copies of the inputs,
         ``svgpfa_elbo_grad``, device->host copies of the bound and the gradients, all on the current
         stream; returns after the stream has drained.  Returns (elbo, h2d_bytes, d2h_bytes)."""
+        if self._rank1():
+            raise NotImplementedError("the host-buffer entry takes Cholesky vectors: ind_points_cov_rep='chol'")
         self._prepare()
         self._select_spike_method(theta_host=io["theta"].numpy(), build=not copy_static)
         dev = self._dev()
@@ -882,7 +943,7 @@ class B200SVLowerBound:
     # the kernel objects' parameter tensors, which alias the same packed buffer -- are NOT part of the state: they
     # are rebuilt from the packed buffers on load, with their requires_grad flags.
     _TRANSIENT = ("_bufs", "_dims", "_desc_host", "_desc_dev", "_ws", "_cached_keepalive", "_pg", "_Z", "_m", "_cv",
-                  "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared", "_pm", "_gsum_key")
+                  "_qv", "_qd", "_cov_key", "_theta", "_leaf_list", "_pending", "_pinned", "_events", "_next_slot", "_kernels", "_last_shared", "_pm", "_gsum_key")
 
     def __getstate__(self):
         self._poll_errors(block=True)
@@ -891,6 +952,8 @@ class B200SVLowerBound:
         st["_kzz_key"] = st["_spike_key"] = st["_vq_key"] = None
         if self._params_set:
             st["_leaf_requires_grad"] = [bool(p.requires_grad) for p in self._leaf_list]
+            if self._rank1():
+                st["_qd_requires_grad"] = [bool(p.requires_grad) for p in list(self._qv) + list(self._qd)]
         if self._kernels is not None:
             kernels = []
             for kern in self._kernels:                 # kernel objects without their (aliasing) parameter tensor
@@ -902,6 +965,7 @@ class B200SVLowerBound:
 
     def __setstate__(self, st):
         flags = st.pop("_leaf_requires_grad", None)
+        qd_flags = st.pop("_qd_requires_grad", None)
         kernels = st.pop("_kernel_states", None)
         self.__dict__.update(st)
         self._pg = None
@@ -924,10 +988,20 @@ class B200SVLowerBound:
             self._refresh_leaf_list()
             for p, flag in zip(self._leaf_list, flags or []):
                 p.requires_grad_(flag)
+            if self._rank1():
+                for p, flag in zip(list(self._qv) + list(self._qd), qd_flags or []):
+                    p.requires_grad_(flag)
 
 
-def buildModelB200(kernels, device=None, process_group=None, shard_mode="auto"):
-    """Sibling of ``SVGPFAModelFactory.buildModelPyTorch(kernels=...)`` for the in-scope model
-    (point process, exponential link, linear embedding, Cholesky Kzz solves, Cholesky-vector
-    covariance; stats/svGPFAModelFactory.py:40-148)."""
-    return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group, shard_mode=shard_mode)
+indPointsCovRank1PlusDiag, indPointsCovChol = 100000, 100001      # the reference's constants (svGPFAModelFactory.py:29-32)
+
+
+def buildModelB200(kernels, device=None, process_group=None, shard_mode="auto", indPointsCovRep=indPointsCovChol):
+    """Sibling of ``SVGPFAModelFactory.buildModelPyTorch(kernels=..., indPointsCovRep=...)`` for the in-scope model
+    (point process, exponential link, linear embedding, Cholesky Kzz solves; variational covariance as Cholesky
+    vectors or rank-1-plus-diagonal; stats/svGPFAModelFactory.py:40-148)."""
+    if indPointsCovRep not in (indPointsCovChol, indPointsCovRank1PlusDiag):
+        raise ValueError("Invalid indPointsCovRep")
+    rep = "rank1_plus_diag" if indPointsCovRep == indPointsCovRank1PlusDiag else "chol"
+    return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group, shard_mode=shard_mode,
+                            ind_points_cov_rep=rep)

@@ -92,3 +92,21 @@ def test_cached_stats_ell():
                                   torch.from_numpy(ref["quad_latent_var"]), mu_s,
                                   torch.from_numpy(case["C"]), torch.from_numpy(case["d"]))
     assert abs(v.item() - float(ref["ell_cached"])) <= 1e-12 * abs(float(ref["ell_cached"]))
+
+
+def test_rank1_plus_diag_fixture():
+    """the rank-1-plus-diagonal covariance parameterisation (svPosteriorOnIndPoints.py:86-119) against the
+    unmodified reference built with indPointsCovRep=indPointsCovRank1PlusDiag (tests/golden/make_rank1.py); and the same
+    covariances through the Cholesky-vector parameterisation give the same bound."""
+    from svgpfa_b200 import synthetic
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "tiny_rank1.npz"))
+    K = len(case["kernel_types"])
+    q = [ref[f"in_q_svec_{k}"] for k in range(K)]
+    d = [ref[f"in_q_sdiag_{k}"] for k in range(K)]
+    out = orc.elbo_and_grads_rank1(case, q, d)
+    for key in ("elbo", "ell", "kl"):
+        assert abs(out[key] - float(ref[key])) <= 1e-13 * abs(float(ref[key]))
+    for key in [k for k in ref if k.startswith("grad_")]:
+        assert rel_err(out[key], ref[key]) <= 1e-11, key
+    std = orc.elbo_and_grads(case)
+    assert abs(std["elbo"] - float(ref["elbo"])) <= 1e-12 * abs(float(ref["elbo"]))
