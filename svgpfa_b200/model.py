@@ -156,9 +156,18 @@ class B200SVLowerBound:
     _stats_serial = 0
 
     def __init__(self, kernels=None, device=None, process_group=None, check_errors=True, shard_mode="auto",
-                 ind_points_cov_rep="chol"):
+                 ind_points_cov_rep="chol", kzz_inv_method="chol"):
         if ind_points_cov_rep not in ("chol", "rank1_plus_diag"):
             raise ValueError("ind_points_cov_rep must be 'chol' or 'rank1_plus_diag'")
+        if kzz_inv_method not in ("chol", "pinv"):
+            raise ValueError("kzz_inv_method must be 'chol' or 'pinv'")
+        # how Kzz^-1 is applied (stats/svGPFAModelFactory.py:25-27).  "pinv" is the reference's IndPointsLocsKMS_PInv
+        # (kernelsMatricesStore.py:146-159: torch.linalg.pinv(Kzz, rcond=1e-15) @ x).  For a Kzz of full numerical rank --
+        # which kappa(Z, Z) + reg I is whenever its Cholesky factorisation exists -- the pseudo-inverse IS the inverse, and
+        # so is its derivative: the variant runs through the same kernels (the reference's two variants agree to 3e-16 on
+        # the bound and 3e-14 on the gradients on the committed fixture).  What is NOT reproduced is the truncation of a
+        # numerically singular Kzz: there the Cholesky fails and the error below is raised.
+        self._kzz_inv_method = kzz_inv_method
         # how the variational covariance S_kr is parameterised (stats/svGPFAModelFactory.py:29-32):
         #   "chol"             Cholesky vectors, S = Ls Ls^T          (SVPosteriorOnIndPointsChol, the default)
         #   "rank1_plus_diag"  S = q q^T + diag(d^2)                  (SVPosteriorOnIndPointsRank1PlusDiag)
@@ -655,7 +664,9 @@ class B200SVLowerBound:
                 self._kzz_key = self._spike_key = self._vq_key = None
                 where = (f"Kzz of trial {int(hdr[6])}, latent {int(hdr[7])} is" if float(hdr[_cabi.SHARED_STATUS]) == 1.0
                          else "a Kzz of more than one trial shard is")
-                raise torch.linalg.LinAlgError(f"linalg.cholesky: {where} not positive-definite")
+                hint = (" (kzz_inv_method='pinv': the truncated pseudo-inverse of a numerically singular Kzz is not "
+                        "reproduced)" if getattr(self, "_kzz_inv_method", "chol") == "pinv" else "")
+                raise torch.linalg.LinAlgError(f"linalg.cholesky: {where} not positive-definite{hint}")
             if math.isinf(float(hdr[0])):
                 warnings.warn("infinity lower bound detected")       # svLowerBound.py:51-53
 
@@ -994,14 +1005,19 @@ class B200SVLowerBound:
 
 
 indPointsCovRank1PlusDiag, indPointsCovChol = 100000, 100001      # the reference's constants (svGPFAModelFactory.py:29-32)
+kernelMatrixInvChol, kernelMatrixInvPInv = 10000, 10001           # (svGPFAModelFactory.py:25-27)
 
 
-def buildModelB200(kernels, device=None, process_group=None, shard_mode="auto", indPointsCovRep=indPointsCovChol):
+def buildModelB200(kernels, device=None, process_group=None, shard_mode="auto", indPointsCovRep=indPointsCovChol,
+                   kernelMatrixInvMethod=kernelMatrixInvChol):
     """Sibling of ``SVGPFAModelFactory.buildModelPyTorch(kernels=..., indPointsCovRep=...)`` for the in-scope model
     (point process, exponential link, linear embedding, Cholesky Kzz solves; variational covariance as Cholesky
     vectors or rank-1-plus-diagonal; stats/svGPFAModelFactory.py:40-148)."""
     if indPointsCovRep not in (indPointsCovChol, indPointsCovRank1PlusDiag):
         raise ValueError("Invalid indPointsCovRep")
+    if kernelMatrixInvMethod not in (kernelMatrixInvChol, kernelMatrixInvPInv):
+        raise ValueError("Invalid kernelMatrixInvMethod")
     rep = "rank1_plus_diag" if indPointsCovRep == indPointsCovRank1PlusDiag else "chol"
+    inv = "pinv" if kernelMatrixInvMethod == kernelMatrixInvPInv else "chol"
     return B200SVLowerBound(kernels=kernels, device=device, process_group=process_group, shard_mode=shard_mode,
-                            ind_points_cov_rep=rep)
+                            ind_points_cov_rep=rep, kzz_inv_method=inv)

@@ -75,3 +75,27 @@ def test_estep_on_q_and_d_improves_the_bound_and_survives_pickling():
     b2, _, _ = ecm.run_step(twin, "estep", kw)                       # the reloaded leaves still drive the kernels
     assert b2 >= b1 - 1e-9 * abs(b1)
     assert stats["allTimes"][0].shape[0] == len(case["spike_counts"])
+
+
+def test_pinv_kzz_store_variant_matches_the_reference():
+    """buildModelB200(kernelMatrixInvMethod=kernelMatrixInvPInv) against the unmodified reference built with
+    IndPointsLocsKMS_PInv (tests/golden/make_pinv.py): full-rank Kzz, same kernels, BASELINE.json's tolerances."""
+    import svgpfa_b200
+    from svgpfa_b200.model import kernelMatrixInvPInv
+    from svgpfa_b200.testing import initial_params_from_case, set_requires_grad, grads_as_dict
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed_pinv.npz"))
+    model = svgpfa_b200.buildModelB200(kernels=svgpfa_b200.build_kernels(case["kernel_types"]),
+                                       kernelMatrixInvMethod=kernelMatrixInvPInv)
+    measurements = [[torch.from_numpy(np.ascontiguousarray(s)) for s in trial] for trial in synthetic.nested_spikes(case)]
+    model.setParamsAndData(measurements=measurements, initial_params=initial_params_from_case(case),
+                           eLLCalculationParams={"leg_quad_points": torch.from_numpy(case["leg_quad_points"]),
+                                                 "leg_quad_weights": torch.from_numpy(case["leg_quad_weights"])},
+                           priorCovRegParam=case["reg"])
+    set_requires_grad(model)
+    v = model.eval()
+    v.backward()
+    assert abs(v.item() - float(ref["elbo"])) <= ELBO_TOL * abs(float(ref["elbo"]))
+    for key, g in grads_as_dict(model).items():
+        assert rel_err(g, ref[key]) <= GRAD_TOL, key
+    with pytest.raises(ValueError):
+        svgpfa_b200.buildModelB200(kernels=svgpfa_b200.build_kernels(case["kernel_types"]), kernelMatrixInvMethod=3)

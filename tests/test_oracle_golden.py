@@ -110,3 +110,15 @@ def test_rank1_plus_diag_fixture():
         assert rel_err(out[key], ref[key]) <= 1e-11, key
     std = orc.elbo_and_grads(case)
     assert abs(std["elbo"] - float(ref["elbo"])) <= 1e-12 * abs(float(ref["elbo"]))
+
+
+def test_pinv_kzz_store_fixture():
+    """the reference built with kernelMatrixInvMethod=kernelMatrixInvPInv (IndPointsLocsKMS_PInv,
+    kernelsMatricesStore.py:146-159; tests/golden/make_pinv.py) on the inputs of tiny_mixed: for a Kzz of full numerical
+    rank (cond <= 30 here) the pseudo-inverse is the inverse, so the restatement with Cholesky solves reproduces it."""
+    case, ref = synthetic.load_case(os.path.join(GOLDEN, "tiny_mixed_pinv.npz"))
+    assert float(ref["kzz_cond_max"]) < 1e3
+    out = orc.elbo_and_grads(case)
+    assert abs(out["elbo"] - float(ref["elbo"])) <= 1e-13 * abs(float(ref["elbo"]))
+    for key in [k for k in ref if k.startswith("grad_")]:
+        assert rel_err(out[key], ref[key]) <= 1e-11, key
