@@ -102,3 +102,30 @@ def test_optimal_start_returns_without_iterating():
 def test_needs_cuda_without_injected_ops():
     with pytest.raises(RuntimeError, match="no CPU path"):
         LBFGS([torch.zeros(3, dtype=F64, requires_grad=True)])
+
+
+@pytest.mark.parametrize("max_iter,max_eval", [(5, 6), (3, 3), (10, 12), (1, 1)])
+def test_evaluation_budget_is_spent_like_torch(max_iter, max_eval):
+    """``max_eval`` caps the line search (``max_ls = max_eval - current_evals``) and ends the step: same number of
+    iterations and closure calls, same points, when the budget binds."""
+    kw = dict(lr=1.0, max_iter=max_iter, max_eval=max_eval, tolerance_grad=1e-12, tolerance_change=1e-14,
+              line_search_fn="strong_wolfe", history_size=4)
+    _, pa = make_params(2, 4, 7, True)
+    _, pb = make_params(2, 4, 7, True)
+    la, ia, ea, xa = run(torch.optim.LBFGS, illcond, pa, 1, **kw)
+    lb, ib, eb, xb = run(lambda p, **k: LBFGS(p, ops=TorchVectorOps(), **k), illcond, pb, 1, **kw)
+    assert (ia, ea) == (ib, eb) and len(la) == len(lb)
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-10 * max(1.0, abs(a))
+    for a, b in zip(xa, xb):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-11)
+
+
+def test_constructor_validation():
+    p = [torch.zeros(3, dtype=F64, requires_grad=True)]
+    with pytest.raises(RuntimeError, match="strong_wolfe"):
+        LBFGS(p, ops=TorchVectorOps(), line_search_fn="armijo")
+    with pytest.raises(ValueError, match="float64"):
+        LBFGS([torch.zeros(3, dtype=torch.float32, requires_grad=True)], ops=TorchVectorOps())
+    with pytest.raises(ValueError, match="learning rate"):
+        LBFGS(p, ops=TorchVectorOps(), lr=-1.0)
